@@ -1,0 +1,74 @@
+"""ctypes binding of libjsd_b200.so (the C ABI declared in include/jsd_b200.h).
+
+There is deliberately no fallback: if the library has not been built, or a
+call fails, this module raises -- the product path never silently drops to
+PyTorch or to the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+from .build import LIB_PATH
+
+# name -> (restype, argtypes); mirrors include/jsd_b200.h one to one
+SIGNATURES = {
+    "jsd_abi_version": (c_int, []),
+    "jsd_last_error": (c_char_p, []),
+    "jsd_sm_count": (c_int, []),
+    "jsd_index_workspace_bytes": (c_size_t, [c_int64]),
+    "jsd_index_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                   c_void_p]),
+    "jsd_transpose_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "jsd_dense_workspace_bytes": (c_size_t, []),
+    "jsd_dense_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "jsd_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "jsd_normalize_bwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "jsd_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                              c_void_p]),
+}
+
+ABI_VERSION = 1
+_lib = None
+
+
+class JSDLibraryError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise JSDLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no PyTorch/CPU fallback for the JSD kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.jsd_abi_version() != ABI_VERSION:
+        raise JSDLibraryError(f"libjsd_b200.so ABI {lib.jsd_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().jsd_last_error().decode("utf-8", "replace")
+        raise JSDLibraryError(f"{what} failed: {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

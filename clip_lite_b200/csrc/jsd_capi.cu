@@ -1,0 +1,340 @@
+// C ABI of libjsd_b200.so (see include/jsd_b200.h): argument checks, TMA tensor-map
+// encoding and kernel launches.  Everything is asynchronous on the caller's stream.
+#include "../../include/jsd_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "jsd_dense.cuh"
+#include "jsd_rowwise.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define JSD_CUDA_OK(expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e_));      \
+  } while (0)
+
+#define JSD_REQUIRE(cond, ...)              \
+  do {                                      \
+    if (!(cond)) return fail(__VA_ARGS__);  \
+  } while (0)
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeFn>(p);
+  return fn;
+}
+
+// bf16 matrix [outer, inner] with row pitch `pitch_elems`; box = box_inner x box_outer, 128B swizzle.
+int make_tmap(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t pitch_elems, int box_inner,
+              int box_outer) {
+  EncodeFn enc = get_encode_fn();
+  JSD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  JSD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  JSD_REQUIRE((pitch_elems * 2) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (got %lld elems)",
+              (long long)pitch_elems);
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  JSD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int sm_count_cached() {
+  static int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+template <int MODE, bool A_MN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const jsd::GemmParams& p, cudaStream_t st,
+                int* grid_out = nullptr) {
+  auto kern = jsd::jsd_gemm_kernel<MODE, A_MN>;
+  static bool configured = false;
+  if (!configured) {
+    JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, jsd::GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  const int sms = sm_count_cached();
+  JSD_REQUIRE(sms > 0, "no CUDA device");
+  const long long tiles = (long long)((p.M + jsd::BLOCK_M - 1) / jsd::BLOCK_M) *
+                          ((p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  if (grid_out) *grid_out = grid;
+  kern<<<grid, jsd::GEMM_THREADS, jsd::GEMM_SMEM_BYTES, st>>>(tmA, tmB, p);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+bool fits_int(int64_t v) { return v > 0 && v < (int64_t)1 << 30; }
+
+template <typename T>
+int launch_index(const void* F, const void* G, int64_t B, int64_t D, const int32_t* neg, const int32_t* iptr,
+                 const int32_t* iidx, const float* t_dev, float* coefp, float* partials, void* dF, void* dG,
+                 cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) |
+                                     reinterpret_cast<uintptr_t>(dF) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0;
+  const int per_thread = vec ? 4 : 1;
+  int threads = 64;
+  while (threads < 256 && threads * per_thread * 2 <= D) threads *= 2;
+  if (vec)
+    jsd::jsd_index_kernel<T, 4><<<(unsigned)B, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr,
+                                                               iidx, t_dev, coefp, partials, (T*)dF, (T*)dG);
+  else
+    jsd::jsd_index_kernel<T, 1><<<(unsigned)B, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr,
+                                                               iidx, t_dev, coefp, partials, (T*)dF, (T*)dG);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int launch_normalize(const void* X, int64_t rows, int64_t D, void* Xn, float* inv_norm, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xn)) & 15) == 0;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (vec)
+    jsd::normalize_cast_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, (__nv_bfloat16*)Xn, inv_norm);
+  else
+    jsd::normalize_cast_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, (__nv_bfloat16*)Xn, inv_norm);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
+                         const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
+                         const float* gamma_dev, float inv_rows, void* dX, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(dX) | reinterpret_cast<uintptr_t>(acc) |
+                     reinterpret_cast<uintptr_t>(partner)) & 15) == 0;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (vec)
+    jsd::normalize_bwd_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
+                                                        (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
+                                                        gamma_dev, inv_rows, (T*)dX);
+  else
+    jsd::normalize_bwd_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
+                                                        (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
+                                                        gamma_dev, inv_rows, (T*)dX);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+#define JSD_DISPATCH_DTYPE(dtype, CALL)                                    \
+  switch (dtype) {                                                         \
+    case JSD_F32: { using T = float; return CALL; }                        \
+    case JSD_BF16: { using T = __nv_bfloat16; return CALL; }               \
+    case JSD_F16: { using T = __half; return CALL; }                       \
+    default: return fail("unsupported dtype code %d", (int)(dtype));       \
+  }
+
+}  // namespace
+
+extern "C" {
+
+int jsd_abi_version(void) { return 1; }
+
+const char* jsd_last_error(void) { return g_err; }
+
+int jsd_sm_count(void) { return sm_count_cached(); }
+
+size_t jsd_index_workspace_bytes(int64_t B) { return (size_t)(B > 0 ? B : 0) * 4 * sizeof(float); }
+
+int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
+                      const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
+                      float* out4, void* dF, void* dG, jsd_stream_t stream) {
+  JSD_REQUIRE(F && G && t_dev && workspace && out4 && dF && dG, "jsd_index_fwd_bwd: null pointer argument");
+  JSD_REQUIRE(fits_int(B) && fits_int(D), "jsd_index_fwd_bwd: B=%lld, D=%lld out of range", (long long)B, (long long)D);
+  JSD_REQUIRE((neg_index == nullptr) == (inv_ptr == nullptr) && (inv_ptr == nullptr) == (inv_idx == nullptr),
+              "jsd_index_fwd_bwd: neg_index, inv_ptr and inv_idx must be given together");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* coefp = (float*)workspace;
+  float* partials = coefp + B;
+  int rc = [&]() -> int {
+    JSD_DISPATCH_DTYPE(dtype, (launch_index<T>(F, G, B, D, neg_index, inv_ptr, inv_idx, t_dev, coefp, partials, dF,
+                                               dG, st)));
+  }();
+  if (rc) return rc;
+  jsd::finalize_kernel<<<1, 256, 0, st>>>(partials, (int)B, 3, 1.0 / (double)B, 1.0 / (double)B, 1.0, 0.0, out4);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int jsd_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                       jsd_stream_t stream) {
+  JSD_REQUIRE(in && out, "jsd_transpose_bf16: null pointer argument");
+  JSD_REQUIRE(fits_int(rows) && fits_int(cols) && ld_in >= cols && ld_out >= rows, "jsd_transpose_bf16: bad shape");
+  dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+  jsd::transpose_bf16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, (int)rows, (int)cols, ld_in, (__nv_bfloat16*)out, ld_out);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn, void* XnT, int64_t ldt,
+                       float* inv_norm, jsd_stream_t stream) {
+  JSD_REQUIRE(X && Xn && inv_norm, "jsd_normalize_cast: null pointer argument");
+  JSD_REQUIRE(fits_int(rows) && fits_int(D), "jsd_normalize_cast: rows=%lld, D=%lld out of range", (long long)rows,
+              (long long)D);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = [&]() -> int { JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(X, rows, D, Xn, inv_norm, st))); }();
+  if (rc) return rc;
+  if (XnT) return jsd_transpose_bf16(Xn, rows, D, D, XnT, ldt, stream);
+  return 0;
+}
+
+size_t jsd_dense_workspace_bytes(void) {
+  return (size_t)1024 * jsd::NUM_EPI_WARPS * jsd::PARTIALS_PER_WARP * sizeof(float);   // up to 1024 CTAs
+}
+
+int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
+                  const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
+                  jsd_stream_t stream) {
+  JSD_REQUIRE(U && V && t_dev && gdiag && workspace && out4, "jsd_dense_fwd: null pointer argument");
+  JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_fwd: M=%lld N=%lld D=%lld out of range",
+              (long long)M, (long long)N, (long long)D);
+  JSD_REQUIRE(D % 8 == 0, "jsd_dense_fwd: D must be a multiple of 8 (got %lld)", (long long)D);
+  JSD_REQUIRE(row_offset >= 0 && row_offset + M <= N, "jsd_dense_fwd: positives [%lld, %lld) outside the %lld columns",
+              (long long)row_offset, (long long)(row_offset + M), (long long)N);
+  if (Gmat) {
+    JSD_REQUIRE(ldg >= N && ldg % 64 == 0, "jsd_dense_fwd: ldg must be a multiple of 64 and >= N");
+    JSD_REQUIRE((reinterpret_cast<uintptr_t>(Gmat) & 15) == 0, "jsd_dense_fwd: Gmat must be 16-byte aligned");
+  }
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap(&tmA, U, D, M, D, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;
+  if (int rc = make_tmap(&tmB, V, D, N, D, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;
+  jsd::GemmParams p{};
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)D;
+  p.n_fastest = 0;
+  p.row_offset = (int)row_offset;
+  p.t_dev = t_dev;
+  p.gmat = (__nv_bfloat16*)Gmat;
+  p.ldg = ldg;
+  p.gdiag = gdiag;
+  p.partials = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = 0;
+  if (int rc = launch_gemm<jsd::MODE_FWD, false>(tmA, tmB, p, st, &grid)) return rc;
+  const double inv_pos = 1.0 / (double)M;
+  const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
+  jsd::finalize_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS,
+                                          jsd::PARTIALS_PER_WARP, inv_pos, inv_neg, inv_pos, inv_neg, out4);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* XT, int64_t ldxt, int64_t M,
+                            int64_t N, int64_t D, const float* t_dev, const float* gamma_dev, float* out,
+                            jsd_stream_t stream) {
+  JSD_REQUIRE(Gmat && XT && t_dev && out, "jsd_dense_bwd: null pointer argument");
+  JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_bwd: M=%lld N=%lld D=%lld out of range",
+              (long long)M, (long long)N, (long long)D);
+  JSD_REQUIRE(D % 4 == 0, "jsd_dense_bwd: D must be a multiple of 4");
+  JSD_REQUIRE(ldg >= N && ldg % 8 == 0, "jsd_dense_bwd: bad ldg");
+  const int64_t kdim = dv ? M : N;     // contraction length
+  const int64_t rows = dv ? N : M;     // rows of the gradient
+  JSD_REQUIRE(ldxt >= kdim && ldxt % 8 == 0, "jsd_dense_bwd: transposed operand pitch must be >= %lld and a multiple of 8",
+              (long long)kdim);
+  CUtensorMap tmA, tmB;
+  if (!dv) {
+    if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;   // [M, N], K = N
+  } else {
+    if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, 64, jsd::BLOCK_K)) return rc;             // MN-major: box 64 j x 64 i
+  }
+  if (int rc = make_tmap(&tmB, XT, kdim, D, ldxt, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;    // [D, kdim]
+  jsd::GemmParams p{};
+  p.M = (int)rows;
+  p.N = (int)D;
+  p.K = (int)kdim;
+  p.n_fastest = 1;
+  p.t_dev = t_dev;
+  p.gamma_dev = gamma_dev;
+  p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;
+  p.out = out;
+  p.ldo = D;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dv ? launch_gemm<jsd::MODE_GRAD, true>(tmA, tmB, p, st) : launch_gemm<jsd::MODE_GRAD, false>(tmA, tmB, p, st);
+}
+
+int jsd_dense_bwd_du(const void* Gmat, int64_t ldg, const void* VT, int64_t ldvt, int64_t M, int64_t N, int64_t D,
+                     const float* t_dev, const float* gamma_dev, float* dUacc, jsd_stream_t stream) {
+  return dense_bwd_common(false, Gmat, ldg, VT, ldvt, M, N, D, t_dev, gamma_dev, dUacc, stream);
+}
+
+int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* UT, int64_t ldut, int64_t M, int64_t N, int64_t D,
+                     const float* t_dev, const float* gamma_dev, float* dVacc, jsd_stream_t stream) {
+  return dense_bwd_common(true, Gmat, ldg, UT, ldut, M, N, D, t_dev, gamma_dev, dVacc, stream);
+}
+
+int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
+                      const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
+                      const float* gamma_dev, int64_t M_rows, void* dX, jsd_stream_t stream) {
+  JSD_REQUIRE(X && inv_norm && acc && partner && t_dev && dX, "jsd_normalize_bwd: null pointer argument");
+  JSD_REQUIRE(fits_int(rows) && fits_int(D) && M_rows > 0, "jsd_normalize_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_rows = (float)(1.0 / (double)M_rows);
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(X, rows, D, inv_norm, acc, partner, partner_offset, gdiag, t_dev,
+                                                     gamma_dev, inv_rows, dX, st)));
+}
+
+int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int64_t M, int64_t N,
+                  int64_t K, float* C, jsd_stream_t stream) {
+  JSD_REQUIRE(A && B && C, "jsd_gemm_bf16: null pointer argument");
+  JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(K), "jsd_gemm_bf16: bad shape");
+  JSD_REQUIRE(N % 4 == 0, "jsd_gemm_bf16: N must be a multiple of 4");
+  CUtensorMap tmA, tmB;
+  if (a_mn_major) {
+    if (int rc = make_tmap(&tmA, A, M, K, lda, 64, jsd::BLOCK_K)) return rc;     // A^T stored [K, lda]
+  } else {
+    if (int rc = make_tmap(&tmA, A, K, M, lda, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;
+  }
+  if (int rc = make_tmap(&tmB, B, K, N, ldb, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;
+  jsd::GemmParams p{};
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.n_fastest = 1;
+  p.t_dev = nullptr;
+  p.gamma_dev = nullptr;
+  p.scale = 1.f;
+  p.out = C;
+  p.ldo = N;
+  cudaStream_t st = (cudaStream_t)stream;
+  return a_mn_major ? launch_gemm<jsd::MODE_GRAD, true>(tmA, tmB, p, st)
+                    : launch_gemm<jsd::MODE_GRAD, false>(tmA, tmB, p, st);
+}
+
+}  // extern "C"

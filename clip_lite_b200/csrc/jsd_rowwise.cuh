@@ -1,0 +1,367 @@
+// HBM-bound row-wise kernels of the JSD hot path:
+//
+//   jsd_index_kernel      the reference's estimator (one indexed negative per row,
+//                         loss.py:94-105,204-254) fused forward + backward
+//   normalize_cast_kernel F.normalize (loss.py:94-95) + cast to bf16 + 1/||x||
+//   transpose_bf16_kernel K-major copy of the normalised operand for the grad GEMMs
+//   normalize_bwd_kernel  diagonal (positive-pair) term + Jacobian of F.normalize
+//   finalize_*_kernel     deterministic fp64 reduction of the per-CTA loss partials
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace jsd {
+
+constexpr float kNormEps = 1e-12f;   // F.normalize default eps
+
+// ------------------------------------------------------------------ typed 4-wide access
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&w.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    uint2 w;
+    w.x = pack_bf16x2(v.x, v.y);
+    w.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = w;
+  }
+};
+template <>
+struct Vec4<__half> {
+  static __device__ __forceinline__ float4 load(const __half* p) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(__half* p, float4 v) {
+    uint2 w;
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    w.x = *reinterpret_cast<const uint32_t*>(&a);
+    w.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = w;
+  }
+};
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// Visit a row 4 elements at a time (VEC=4: 16 B-aligned vector access) or one at a time.
+template <typename T, int VEC, typename Fn>
+__device__ __forceinline__ void for_row(int D, int tid, int nthreads, Fn fn) {
+  if constexpr (VEC == 4) {
+    for (int d = tid * 4; d < D; d += nthreads * 4) fn(d);
+  } else {
+    for (int d = tid; d < D; d += nthreads) fn(d);
+  }
+}
+
+// Sum NV per-thread values over the block; every thread gets the totals.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch /* [NV*32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();   // scratch may still be read from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += scratch[i * 32 + w];
+    v[i] = s;
+  }
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+// ------------------------------------------------------------------ index mode
+// One CTA per row j.  Computes everything row j of dF and dG needs:
+//   positive pair (j, j), row j's negative (j, n = neg[j]) and the pairs (p, j)
+//   of every row p whose negative is j (CSR inverse; NULL => p = j-1, the
+//   roll-by-one of loss.py:214-216).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D, const int* __restrict__ neg_index,
+                 const int* __restrict__ inv_ptr, const int* __restrict__ inv_idx, const float* __restrict__ t_dev,
+                 float* __restrict__ coefp, float* __restrict__ partials, T* __restrict__ dF, T* __restrict__ dG) {
+  __shared__ float scratch[5 * 32];
+  const int j = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n = neg_index ? neg_index[j] : (j + 1 == B ? 0 : j + 1);
+  const float tau = expf(*t_dev);
+  const float invB = 1.f / (float)B;
+  const T* fj = F + (size_t)j * D;
+  const T* gj = G + (size_t)j * D;
+  const T* gn = G + (size_t)n * D;
+
+  float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // ff, gg, fg, gngn, fgn
+  for_row<T, VEC>(D, tid, nt, [&](int d) {
+    if constexpr (VEC == 4) {
+      const float4 f = Vec4<T>::load(fj + d), g = Vec4<T>::load(gj + d), h = Vec4<T>::load(gn + d);
+      s5[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+      s5[1] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+      s5[2] += f.x * g.x + f.y * g.y + f.z * g.z + f.w * g.w;
+      s5[3] += h.x * h.x + h.y * h.y + h.z * h.z + h.w * h.w;
+      s5[4] += f.x * h.x + f.y * h.y + f.z * h.z + f.w * h.w;
+    } else {
+      const float f = to_f32(fj[d]), g = to_f32(gj[d]), h = to_f32(gn[d]);
+      s5[0] += f * f;
+      s5[1] += g * g;
+      s5[2] += f * g;
+      s5[3] += h * h;
+      s5[4] += f * h;
+    }
+  });
+  block_sum<5>(s5, scratch);
+  const float inv_f = 1.f / fmaxf(sqrtf(s5[0]), kNormEps);
+  const float inv_g = 1.f / fmaxf(sqrtf(s5[1]), kNormEps);
+  const float inv_gn = 1.f / fmaxf(sqrtf(s5[3]), kNormEps);
+  const float s_pos = tau * s5[2] * inv_f * inv_g;
+  const float s_neg = tau * s5[4] * inv_f * inv_gn;
+  const float a = -sigmoid_f(-s_pos) * invB;   // dL/ds_pos
+  const float b = sigmoid_f(s_neg) * invB;     // dL/ds_neg
+  const float udot = a * s_pos + b * s_neg;    // <u_j, dU_j>
+
+  // rows p that use text row j as their negative
+  int pbeg, pend;
+  if (inv_ptr) {
+    pbeg = inv_ptr[j];
+    pend = inv_ptr[j + 1];
+  } else {
+    pbeg = 0;
+    pend = 1;
+  }
+  float vdot = a * s_pos;   // <v_j, dV_j>
+  for (int k = pbeg; k < pend; ++k) {
+    const int pr = inv_idx ? inv_idx[k] : (j == 0 ? B - 1 : j - 1);
+    const T* fp = F + (size_t)pr * D;
+    float s2[2] = {0.f, 0.f};   // fpfp, fp.gj
+    for_row<T, VEC>(D, tid, nt, [&](int d) {
+      if constexpr (VEC == 4) {
+        const float4 f = Vec4<T>::load(fp + d), g = Vec4<T>::load(gj + d);
+        s2[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+        s2[1] += f.x * g.x + f.y * g.y + f.z * g.z + f.w * g.w;
+      } else {
+        const float f = to_f32(fp[d]), g = to_f32(gj[d]);
+        s2[0] += f * f;
+        s2[1] += f * g;
+      }
+    });
+    block_sum<2>(s2, scratch);
+    const float inv_fp = 1.f / fmaxf(sqrtf(s2[0]), kNormEps);
+    const float sp = tau * s2[1] * inv_fp * inv_g;
+    const float bp = sigmoid_f(sp) * invB;
+    vdot += bp * sp;
+    if (tid == 0) coefp[pr] = tau * bp * inv_fp;   // each p has exactly one target row => no race
+  }
+  __syncthreads();
+
+  T* dfj = dF + (size_t)j * D;
+  T* dgj = dG + (size_t)j * D;
+  const float ca = tau * a, cb = tau * b;
+  for_row<T, VEC>(D, tid, nt, [&](int d) {
+    if constexpr (VEC == 4) {
+      const float4 f = Vec4<T>::load(fj + d), g = Vec4<T>::load(gj + d), h = Vec4<T>::load(gn + d);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = pbeg; k < pend; ++k) {
+        const int pr = inv_idx ? inv_idx[k] : (j == 0 ? B - 1 : j - 1);
+        const float c = coefp[pr];
+        const float4 q = Vec4<T>::load(F + (size_t)pr * D + d);
+        acc.x = fmaf(c, q.x, acc.x);
+        acc.y = fmaf(c, q.y, acc.y);
+        acc.z = fmaf(c, q.z, acc.z);
+        acc.w = fmaf(c, q.w, acc.w);
+      }
+      float4 of, og;
+#define JSD_IDX_ELT(c)                                                            \
+  {                                                                               \
+    const float u = f.c * inv_f, v = g.c * inv_g, vn = h.c * inv_gn;              \
+    of.c = (ca * v + cb * vn - u * udot) * inv_f;                                 \
+    og.c = (ca * u + acc.c - v * vdot) * inv_g;                                   \
+  }
+      JSD_IDX_ELT(x) JSD_IDX_ELT(y) JSD_IDX_ELT(z) JSD_IDX_ELT(w)
+#undef JSD_IDX_ELT
+      Vec4<T>::store(dfj + d, of);
+      Vec4<T>::store(dgj + d, og);
+    } else {
+      const float f = to_f32(fj[d]), g = to_f32(gj[d]), h = to_f32(gn[d]);
+      float acc = 0.f;
+      for (int k = pbeg; k < pend; ++k) {
+        const int pr = inv_idx ? inv_idx[k] : (j == 0 ? B - 1 : j - 1);
+        acc = fmaf(coefp[pr], to_f32(F[(size_t)pr * D + d]), acc);
+      }
+      const float u = f * inv_f, v = g * inv_g, vn = h * inv_gn;
+      dfj[d] = from_f32<T>((ca * v + cb * vn - u * udot) * inv_f);
+      dgj[d] = from_f32<T>((ca * u + acc - v * vdot) * inv_g);
+    }
+  });
+  if (tid == 0) {
+    partials[3 * (size_t)j + 0] = softplus_f(-s_pos);
+    partials[3 * (size_t)j + 1] = softplus_f(s_neg);
+    partials[3 * (size_t)j + 2] = udot;
+  }
+}
+
+// out4 = {pos, neg, pos + neg, dL/dt}; deterministic (fixed order, fp64).
+__global__ void __launch_bounds__(256)
+finalize_kernel(const float* __restrict__ partials, int n, int width, double inv0, double inv1, double inv2,
+                double inv3, float* __restrict__ out4) {
+  __shared__ double sh[4][256];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += 256)
+    for (int k = 0; k < width; ++k) acc[k] += (double)partials[(size_t)i * width + k];
+  for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double pos = sh[0][0] * inv0, neg = sh[1][0] * inv1;
+    const double dt = sh[2][0] * inv2 + sh[3][0] * inv3;
+    out4[0] = (float)pos;
+    out4[1] = (float)neg;
+    out4[2] = (float)(pos + neg);
+    out4[3] = (float)dt;
+  }
+}
+
+// ------------------------------------------------------------------ normalise + cast (dense pre-pass)
+// One warp per row: Xn = bf16(x / max(||x||, eps)), inv_norm = 1 / max(||x||, eps).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_cast_kernel(const T* __restrict__ X, int rows, int D, __nv_bfloat16* __restrict__ Xn,
+                      float* __restrict__ inv_norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* x = X + (size_t)row * D;
+  float ss = 0.f;
+  for_row<T, VEC>(D, lane, 32, [&](int d) {
+    if constexpr (VEC == 4) {
+      const float4 f = Vec4<T>::load(x + d);
+      ss += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+    } else {
+      const float f = to_f32(x[d]);
+      ss += f * f;
+    }
+  });
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), kNormEps);
+  __nv_bfloat16* o = Xn + (size_t)row * D;
+  for_row<T, VEC>(D, lane, 32, [&](int d) {
+    if constexpr (VEC == 4) {
+      const float4 f = Vec4<T>::load(x + d);
+      Vec4<__nv_bfloat16>::store(o + d, make_float4(f.x * inv, f.y * inv, f.z * inv, f.w * inv));
+    } else {
+      o[d] = __float2bfloat16_rn(to_f32(x[d]) * inv);
+    }
+  });
+  if (lane == 0) inv_norm[row] = inv;
+}
+
+// out[c, r] = in[r, c] for bf16 matrices (64 x 64 tiles, block (32, 8)).
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int cols, long long ld_in,
+                      __nv_bfloat16* __restrict__ out, long long ld_out) {
+  __shared__ __nv_bfloat16 t[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 64; r += 8) {
+    const int gr = r0 + r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gc = c0 + 2 * tx + h;
+      t[r][2 * tx + h] = (gr < rows && gc < cols) ? in[(size_t)gr * ld_in + gc] : __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8) {
+    const int gc = c0 + c;
+    if (gc >= cols) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gr = r0 + 2 * tx + h;
+      if (gr < rows) out[(size_t)gc * ld_out + gr] = t[2 * tx + h][c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ normalise backward (dense post-pass)
+// dU_row = acc_row + coef * gdiag[row] * partner[row + partner_offset]      (positive-pair term, fp32)
+// dX_row = (dU_row - u_row <u_row, dU_row>) * inv_norm[row],  u_row = x_row * inv_norm[row]
+// coef = gamma * tau / M_rows.  One warp per row.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __restrict__ inv_norm,
+                     const float* __restrict__ acc, const __nv_bfloat16* __restrict__ partner,
+                     long long partner_offset, const float* __restrict__ gdiag, const float* __restrict__ t_dev,
+                     const float* __restrict__ gamma_dev, float inv_rows, T* __restrict__ dX) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float gamma = gamma_dev ? *gamma_dev : 1.f;
+  const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
+  const float inv = inv_norm[row];
+  const T* x = X + (size_t)row * D;
+  const float* a = acc + (size_t)row * D;
+  const __nv_bfloat16* pr = partner + (size_t)(row + partner_offset) * D;
+  float dot = 0.f;
+  for_row<T, VEC>(D, lane, 32, [&](int d) {
+    if constexpr (VEC == 4) {
+      const float4 f = Vec4<T>::load(x + d), g = Vec4<float>::load(a + d), q = Vec4<__nv_bfloat16>::load(pr + d);
+      dot += f.x * fmaf(c, q.x, g.x) + f.y * fmaf(c, q.y, g.y) + f.z * fmaf(c, q.z, g.z) + f.w * fmaf(c, q.w, g.w);
+    } else {
+      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), a[d]);
+    }
+  });
+  dot = warp_sum(dot) * inv;   // <u, dU>
+  T* o = dX + (size_t)row * D;
+  for_row<T, VEC>(D, lane, 32, [&](int d) {
+    if constexpr (VEC == 4) {
+      const float4 f = Vec4<T>::load(x + d), g = Vec4<float>::load(a + d), q = Vec4<__nv_bfloat16>::load(pr + d);
+      float4 r;
+      r.x = (fmaf(c, q.x, g.x) - f.x * inv * dot) * inv;
+      r.y = (fmaf(c, q.y, g.y) - f.y * inv * dot) * inv;
+      r.z = (fmaf(c, q.z, g.z) - f.z * inv * dot) * inv;
+      r.w = (fmaf(c, q.w, g.w) - f.w * inv * dot) * inv;
+      Vec4<T>::store(o + d, r);
+    } else {
+      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), a[d]) - to_f32(x[d]) * inv * dot) * inv);
+    }
+  });
+}
+
+}  // namespace jsd

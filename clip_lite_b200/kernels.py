@@ -1,0 +1,209 @@
+"""Tensor-level wrappers over the C ABI: one Python function per entry point of
+include/jsd_b200.h.  Inputs are CUDA tensors; pointers, sizes and the current
+CUDA stream are handed to libjsd_b200.so.  Nothing here computes anything in
+PyTorch -- allocation and plumbing only."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected float32, bfloat16 or float16") from None
+
+
+def _req(t: torch.Tensor, name: str, dtype=None, ndim: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the JSD kernels have no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must be {ndim}-dimensional, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _scalar(t: torch.Tensor, name: str) -> torch.Tensor:
+    """Device fp32 scalar (0-dim or 1-element) passed by pointer."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on the GPU")
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.reshape(1).contiguous()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def sm_count() -> int:
+    return _lib.load().jsd_sm_count()
+
+
+# ------------------------------------------------------------------ index mode
+def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[torch.Tensor] = None,
+                  inv_ptr: Optional[torch.Tensor] = None, inv_idx: Optional[torch.Tensor] = None):
+    """Reference-semantics estimator, fused fwd+bwd.  Returns (out4, dF, dG):
+    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), dF/dG for upstream gradient 1."""
+    _req(f, "F", ndim=2)
+    _req(g, "G", dtype=f.dtype, ndim=2)
+    if f.shape != g.shape:
+        raise ValueError(f"F {tuple(f.shape)} and G {tuple(g.shape)} must have the same shape")
+    b, d = f.shape
+    if b == 0 or d == 0:
+        raise ValueError("empty batch")
+    for name, ix, n in (("neg_index", neg_index, b), ("inv_ptr", inv_ptr, b + 1), ("inv_idx", inv_idx, b)):
+        if ix is not None:
+            _req(ix, name, dtype=torch.int32, ndim=1)
+            if ix.numel() != n:
+                raise ValueError(f"{name} must have {n} entries")
+    tt = _scalar(t, "temperature")
+    lib = _lib.load()
+    ws = torch.empty(lib.jsd_index_workspace_bytes(b) // 4, dtype=torch.float32, device=f.device)
+    out4 = torch.empty(4, dtype=torch.float32, device=f.device)
+    df = torch.empty_like(f)
+    dg = torch.empty_like(g)
+    with torch.cuda.device(f.device):
+        _lib.call("jsd_index_fwd_bwd", _ptr(f), _ptr(g), _code(f), b, d, _ptr(neg_index), _ptr(inv_ptr),
+                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(df), _ptr(dg), _stream())
+    return out4, df, dg
+
+
+# ------------------------------------------------------------------ dense mode
+def normalize_cast(x: torch.Tensor, transpose: bool = False):
+    """(Xn bf16 [rows, D], XnT bf16 [D, ldt] or None, inv_norm fp32 [rows])."""
+    _req(x, "X", ndim=2)
+    rows, d = x.shape
+    xn = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    xt = None
+    ldt = 0
+    if transpose:
+        ldt = round_up(rows, 8)
+        xt = torch.empty(d, ldt, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("jsd_normalize_cast", _ptr(x), _code(x), rows, d, _ptr(xn), _ptr(xt), ldt, _ptr(inv), _stream())
+    return xn, xt, inv
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[rows, cols] bf16 -> [cols, round_up(rows, 8)] bf16."""
+    _req(x, "X", dtype=torch.bfloat16, ndim=2)
+    rows, cols = x.shape
+    ldo = round_up(rows, 8)
+    out = torch.empty(cols, ldo, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("jsd_transpose_bf16", _ptr(x), rows, cols, cols, _ptr(out), ldo, _stream())
+    return out
+
+
+def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int = 0, want_grad: bool = True):
+    """Row-slab dense forward.  Returns (out4, Gmat or None, gdiag)."""
+    _req(u, "U", dtype=torch.bfloat16, ndim=2)
+    _req(v, "V", dtype=torch.bfloat16, ndim=2)
+    m, d = u.shape
+    n, d2 = v.shape
+    if d != d2:
+        raise ValueError(f"U and V disagree on D: {d} vs {d2}")
+    tt = _scalar(t, "temperature")
+    lib = _lib.load()
+    ws = torch.empty(lib.jsd_dense_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
+    out4 = torch.empty(4, dtype=torch.float32, device=u.device)
+    gdiag = torch.empty(m, dtype=torch.float32, device=u.device)
+    gmat = None
+    ldg = 0
+    if want_grad:
+        ldg = round_up(n, 64)
+        gmat = torch.empty(m, ldg, dtype=torch.bfloat16, device=u.device)
+    with torch.cuda.device(u.device):
+        _lib.call("jsd_dense_fwd", _ptr(u), _ptr(v), m, n, d, row_offset, _ptr(tt), _ptr(gmat), ldg, _ptr(gdiag),
+                  _ptr(ws), _ptr(out4), _stream())
+    return out4, gmat, gdiag
+
+
+def dense_bwd_du(gmat: torch.Tensor, vt: torch.Tensor, n: int, t: torch.Tensor,
+                 gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dUacc [M, D] fp32 = gamma tau / (M (N-1)) Gmat . V, with vt = V^T [D, ldvt]."""
+    _req(gmat, "Gmat", dtype=torch.bfloat16, ndim=2)
+    _req(vt, "VT", dtype=torch.bfloat16, ndim=2)
+    m, ldg = gmat.shape
+    d, ldvt = vt.shape
+    tt = _scalar(t, "temperature")
+    gg = None if gamma is None else _scalar(gamma, "gamma")
+    out = torch.empty(m, d, dtype=torch.float32, device=gmat.device)
+    with torch.cuda.device(gmat.device):
+        _lib.call("jsd_dense_bwd_du", _ptr(gmat), ldg, _ptr(vt), ldvt, m, n, d, _ptr(tt), _ptr(gg), _ptr(out), _stream())
+    return out
+
+
+def dense_bwd_dv(gmat: torch.Tensor, ut: torch.Tensor, n: int, t: torch.Tensor,
+                 gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dVacc [N, D] fp32 = gamma tau / (M (N-1)) Gmat^T . U, with ut = U^T [D, ldut]."""
+    _req(gmat, "Gmat", dtype=torch.bfloat16, ndim=2)
+    _req(ut, "UT", dtype=torch.bfloat16, ndim=2)
+    m, ldg = gmat.shape
+    d, ldut = ut.shape
+    tt = _scalar(t, "temperature")
+    gg = None if gamma is None else _scalar(gamma, "gamma")
+    out = torch.empty(n, d, dtype=torch.float32, device=gmat.device)
+    with torch.cuda.device(gmat.device):
+        _lib.call("jsd_dense_bwd_dv", _ptr(gmat), ldg, _ptr(ut), ldut, m, n, d, _ptr(tt), _ptr(gg), _ptr(out), _stream())
+    return out
+
+
+def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, partner: torch.Tensor,
+                  partner_offset: int, gdiag: Optional[torch.Tensor], t: torch.Tensor,
+                  gamma: Optional[torch.Tensor], m_rows: int) -> torch.Tensor:
+    """Positive-pair term + Jacobian of F.normalize; returns dX in x's dtype."""
+    _req(x, "X", ndim=2)
+    rows, d = x.shape
+    _req(inv_norm, "inv_norm", dtype=torch.float32, ndim=1)
+    _req(acc, "acc", dtype=torch.float32, ndim=2)
+    _req(partner, "partner", dtype=torch.bfloat16, ndim=2)
+    if acc.shape != x.shape or partner.shape[1] != d or partner.shape[0] < rows + partner_offset:
+        raise ValueError("normalize_bwd: shape mismatch")
+    if gdiag is not None:
+        _req(gdiag, "gdiag", dtype=torch.float32, ndim=1)
+    tt = _scalar(t, "temperature")
+    gg = None if gamma is None else _scalar(gamma, "gamma")
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.call("jsd_normalize_bwd", _ptr(x), _code(x), rows, d, _ptr(inv_norm), _ptr(acc), _ptr(partner),
+                  partner_offset, _ptr(gdiag), _ptr(tt), _ptr(gg), m_rows, _ptr(dx), _stream())
+    return dx
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False) -> torch.Tensor:
+    """C [M, N] fp32 = A . B^T on the tcgen05 kernel.  a is [M, K] (K-major) or,
+    with a_mn_major, A^T stored [K, M]; b is [N, K]."""
+    _req(a, "A", dtype=torch.bfloat16, ndim=2)
+    _req(b, "B", dtype=torch.bfloat16, ndim=2)
+    if a_mn_major:
+        k, m = a.shape
+    else:
+        m, k = a.shape
+    n, k2 = b.shape
+    if k != k2:
+        raise ValueError("gemm_bf16: K mismatch")
+    out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("jsd_gemm_bf16", _ptr(a), a.shape[1], int(a_mn_major), _ptr(b), k, m, n, k, _ptr(out), _stream())
+    return out

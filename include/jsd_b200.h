@@ -1,0 +1,115 @@
+/* C ABI of the B200-native JSD contrastive-loss hot path (libjsd_b200.so).
+ *
+ * The reference (4m4n5/CLIP-Lite) has no FFI: its boundary for this path is the
+ * Python class JSDInfoMaxLoss (loss.py:110-314), registered as
+ * LossFactory.PRODUCTS["jsd"] (factories.py:374-376) and called from
+ * model.py:94-101.  The entry points below are what a ctypes binding inside that
+ * class calls in place of the PyTorch ops of loss.py:94-105 (normalise + row dot
+ * * exp(t)), loss.py:204-254 (softplus / mean / roll-by-one negatives) and their
+ * autograd backward (entered from train.py:218).  See INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch-allocated);
+ *    matrices are row-major and contiguous unless a pitch ("ld", in elements) is given;
+ *  - `stream` is a cudaStream_t; all work is enqueued asynchronously on it, the
+ *    library never synchronises and keeps no mutable global state besides the
+ *    last error string (thread-local);
+ *  - scalars that live on the device in the reference (the `temperature`
+ *    parameter, the upstream gradient) are passed as device pointers so that no
+ *    call forces a host round-trip;
+ *  - return value 0 = success; non-zero = error, message from jsd_last_error().
+ *    The library never throws and never falls back to the CPU.
+ */
+#ifndef JSD_B200_H_
+#define JSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* jsd_stream_t; /* cudaStream_t */
+
+enum jsd_dtype { JSD_F32 = 0, JSD_BF16 = 1, JSD_F16 = 2 };
+
+/* ABI version of this header (bumped on any signature change). */
+int jsd_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* jsd_last_error(void);
+/* Number of SMs of the current device (the persistent kernels launch one CTA each). */
+int jsd_sm_count(void);
+
+/* ------------------------------------------------------------------ index mode
+ * The reference's estimator, fused forward + backward.
+ *   replaces: GlobalDiscriminatorDot.forward loss.py:94-105 (called twice, :206-222),
+ *             JSDInfoMaxLoss.forward normal mode loss.py:204-222,254, cluster mode
+ *             loss.py:225-252 (through neg_index), SSL call sites loss.py:257-300,
+ *             and the autograd backward of all of it.
+ * F, G       [B, D] features AFTER the projection heads, dtype `dtype`
+ * neg_index  [B] int32 column of each row's negative, or NULL for (i+1) mod B
+ * inv_ptr/inv_idx  CSR inverse of neg_index ([B+1] / [B]); both NULL iff neg_index is NULL
+ * t_dev      device scalar: the `temperature` parameter (tau = exp(t))
+ * workspace  >= jsd_index_workspace_bytes(B) bytes
+ * out4       device float[4]: {mean softplus(-s_pos), mean softplus(s_neg), their sum, dL/dt}
+ * dF, dG     [B, D] dL/dF, dL/dG for upstream gradient 1 (same dtype as F, G)
+ */
+size_t jsd_index_workspace_bytes(int64_t B);
+int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
+                      const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
+                      float* out4, void* dF, void* dG, jsd_stream_t stream);
+
+/* ------------------------------------------------------------------ dense mode
+ * All off-diagonal pairs as negatives (BASELINE.json north star); a row slab
+ * [M rows] x [N columns] of the global score matrix, positives on column
+ * row_offset + i.  Forward and backward are separate calls so that they sit in
+ * autograd's forward / backward.
+ */
+
+/* F.normalize (loss.py:94-95) + cast: Xn = bf16(x / max(||x||, 1e-12)), inv_norm = 1 / max(||x||, 1e-12).
+ * XnT (optional, may be NULL) receives the transpose [D, ldt] (ldt >= rows, multiple of 8). */
+int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn_bf16, void* XnT_bf16,
+                       int64_t ldt, float* inv_norm, jsd_stream_t stream);
+
+/* Transposed bf16 copy: out[c, r] = in[r, c] (used for the gathered operand in the multi-GPU path). */
+int jsd_transpose_bf16(const void* in_bf16, int64_t rows, int64_t cols, int64_t ld_in, void* out_bf16,
+                       int64_t ld_out, jsd_stream_t stream);
+
+size_t jsd_dense_workspace_bytes(void);
+
+/* Forward: S = tau U V^T on tcgen05 tensor cores, softplus/sigmoid epilogue, S never stored.
+ * U [M, D], V [N, D] bf16 unit rows (D % 8 == 0).  Gmat (optional, NULL => loss only)
+ * [M, ldg] bf16 receives sigma(S_ij) with 0 on the positives (ldg % 64 == 0, ldg >= N);
+ * gdiag [M] receives -sigma(-S_ii').  out4 = {pos, neg, pos + neg, dL/dt} of
+ *   L = mean_i softplus(-S_ii') + (1 / (M (N - 1))) sum_{j != i'} softplus(S_ij). */
+int jsd_dense_fwd(const void* U_bf16, const void* V_bf16, int64_t M, int64_t N, int64_t D, int64_t row_offset,
+                  const float* t_dev, void* Gmat_bf16, int64_t ldg, float* gdiag, void* workspace, float* out4,
+                  jsd_stream_t stream);
+
+/* Backward contractions (tensor cores), off-diagonal part, fp32 out:
+ *   dUacc [M, D] = gamma tau / (M (N-1)) * Gmat   . V     (VT_bf16 = V^T [D, ldvt], ldvt >= N)
+ *   dVacc [N, D] = gamma tau / (M (N-1)) * Gmat^T . U     (UT_bf16 = U^T [D, ldut], ldut >= M)
+ * gamma_dev: device scalar upstream gradient (NULL => 1). */
+int jsd_dense_bwd_du(const void* Gmat_bf16, int64_t ldg, const void* VT_bf16, int64_t ldvt, int64_t M, int64_t N,
+                     int64_t D, const float* t_dev, const float* gamma_dev, float* dUacc, jsd_stream_t stream);
+int jsd_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* UT_bf16, int64_t ldut, int64_t M, int64_t N,
+                     int64_t D, const float* t_dev, const float* gamma_dev, float* dVacc, jsd_stream_t stream);
+
+/* Positive-pair term + Jacobian of F.normalize:
+ *   d_row = acc_row + gamma tau / M_rows * gdiag[row] * partner[row + partner_offset]
+ *   dX_row = (d_row - u_row <u_row, d_row>) * inv_norm[row],   u_row = X_row * inv_norm[row]
+ * X, dX [rows, D] in `dtype`; acc fp32 [rows, D]; partner bf16 [*, D]; gdiag may be NULL (no positive term). */
+int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
+                      const void* partner_bf16, int64_t partner_offset, const float* gdiag, const float* t_dev,
+                      const float* gamma_dev, int64_t M_rows, void* dX, jsd_stream_t stream);
+
+/* Plain C = A . B^T on the same tcgen05 kernel (fp32 out [M, N]); A [M, K] bf16 (a_mn_major = 0)
+ * or A^T [K, lda] (a_mn_major = 1), B [N, K] bf16.  Exposed for the unit tests of the tensor-core path. */
+int jsd_gemm_bf16(const void* A_bf16, int64_t lda, int a_mn_major, const void* B_bf16, int64_t ldb, int64_t M,
+                  int64_t N, int64_t K, float* C, jsd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSD_B200_H_ */

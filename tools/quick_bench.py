@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Stage-by-stage timing of the dense pipeline (development aid; bench.py is the contract)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from clip_lite_b200 import kernels as K  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    shapes = [(8192, 1024), (1024, 1024), (1024, 128), (16384, 512)]
+    if len(sys.argv) > 2:
+        shapes = [(int(sys.argv[1]), int(sys.argv[2]))]
+    for b, d in shapes:
+        f = torch.randn(b, d, device="cuda").bfloat16()
+        g = (0.6 * f.float() + 0.8 * torch.randn(b, d, device="cuda")).bfloat16()
+        t = torch.tensor(2.6593, device="cuda")
+        gamma = torch.tensor(0.9, device="cuda")
+        u, ut, inv_f = K.normalize_cast(f, transpose=True)
+        v, vt, inv_g = K.normalize_cast(g, transpose=True)
+        out4, gmat, gdiag = K.dense_fwd(u, v, t)
+        du = K.dense_bwd_du(gmat, vt, b, t, gamma)
+        dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+        flops = 2.0 * b * b * d
+
+        def full():
+            u, ut, inv_f = K.normalize_cast(f, transpose=True)
+            v, vt, inv_g = K.normalize_cast(g, transpose=True)
+            out4, gmat, gdiag = K.dense_fwd(u, v, t)
+            du = K.dense_bwd_du(gmat, vt, b, t, gamma)
+            dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+            K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b)
+            K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)
+
+        stages = {
+            "normalize_cast+T x2": lambda: (K.normalize_cast(f, True), K.normalize_cast(g, True)),
+            "dense_fwd": lambda: K.dense_fwd(u, v, t),
+            "dense_fwd(loss only)": lambda: K.dense_fwd(u, v, t, want_grad=False),
+            "bwd_du": lambda: K.dense_bwd_du(gmat, vt, b, t, gamma),
+            "bwd_dv": lambda: K.dense_bwd_dv(gmat, ut, b, t, gamma),
+            "normalize_bwd x2": lambda: (K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b),
+                                         K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)),
+            "FULL fwd+bwd": full,
+        }
+        print(f"== B={b} D={d}  (2*B*B*D = {flops/1e9:.1f} GFLOP per GEMM)")
+        for name, fn in stages.items():
+            med, mn = timeit(fn)
+            extra = ""
+            if name in ("dense_fwd", "dense_fwd(loss only)", "bwd_du", "bwd_dv"):
+                extra = f"  {flops/ (med*1e-3)/1e12:8.1f} TFLOP/s"
+            if name == "FULL fwd+bwd":
+                extra = f"  {3*flops/(med*1e-3)/1e12:8.1f} TFLOP/s (6B^2D)  {b/(med*1e-3)/1e6:.2f} Mpairs/s"
+            print(f"  {name:24s} median {med*1e3:9.1f} us   min {mn*1e3:9.1f} us{extra}")
+        # cuBLAS reference for the same GEMM shape
+        a32 = u
+        med, mn = timeit(lambda: torch.matmul(a32, v.t()))
+        print(f"  {'torch.matmul U@V.T bf16':24s} median {med*1e3:9.1f} us   min {mn*1e3:9.1f} us  {flops/(med*1e-3)/1e12:8.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the JSD-loss hot path (BASELINE.json metric: fwd+bwd image-text pairs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one forward + backward of the dense JSD estimator over one batch of
+synthetic embeddings (N(0,1) features, text correlated 0.6 with the image,
+pre-normalised, bf16, resident in HBM), through the public API
+(clip_lite_b200.ops.jsd_dense_loss, or parallel.gathered_dense_loss for N > 1).
+
+Workloads
+  dense_b8192_d1024 (default)  global batch 8192, D = 1024 -- the configuration the north-star
+                               target is quoted on; for N > 1 the same global batch is sharded
+                               B/N rows per GPU with all-gather + reduce-scatter ("strong")
+  weak1024_d1024               1024 rows per GPU, global batch 1024*N (BASELINE configs[2])
+  dense_b1024_d1024 / dense_b1024_d128   BASELINE configs[1] (launch-latency-bound)
+  stress_b65536_d512           BASELINE configs[3] (needs N >= 2 for the 180 GB budget at N=1 it fits too)
+
+Prints ONE JSON line on rank 0 (see the task contract): value = device-resident throughput,
+e2e = the same through host (pinned) buffers with H2D/D2H inside the timed region, roofline for
+the tcgen05 GEMM family, cpu_baseline = the oracle restatement timed on the host cores.
+`--impl reference` times the reference's CPU path (PyTorch fp32 restatement of loss.py's
+estimator in its dense form: the reference tree itself cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "jsd_loss_fwd_bwd_pairs_per_s"
+UNIT = "pairs/s"
+WORKLOADS = {
+    #  name                : (global batch at N=1, D, rows-per-gpu fixed?)
+    "dense_b8192_d1024": dict(batch=8192, dim=1024, weak=False),
+    "weak1024_d1024": dict(batch=1024, dim=1024, weak=True),
+    "dense_b1024_d1024": dict(batch=1024, dim=1024, weak=False),
+    "dense_b1024_d128": dict(batch=1024, dim=128, weak=False),
+    "stress_b65536_d512": dict(batch=65536, dim=512, weak=False),
+}
+T_INIT = 2.659260036932778   # log(1/0.07), loss.py:82
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
+        except Exception:
+            pass
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth(batch, dim, seed=0):
+    """SURVEY 8d synthetic inputs: correlated pairs, pre-normalised, bf16."""
+    gen = torch.Generator("cpu").manual_seed(seed)
+    f0 = torch.randn(batch, dim, generator=gen)
+    g0 = torch.randn(batch, dim, generator=gen)
+    g = 0.6 * f0 + 0.8 * g0
+    f = torch.nn.functional.normalize(f0, dim=-1).bfloat16()
+    g = torch.nn.functional.normalize(g, dim=-1).bfloat16()
+    return f, g
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.bits, self.max_mhz, self._stop = [], 0, None, threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                try:
+                    self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        reasons = [n for b, n in self.REASONS.items() if self.bits & b and n != "gpu_idle"]
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU (reference) arm
+def cpu_dense_step(f, g, t, row_offset=0):
+    """fwd + backward() of the fp32 restatement, exactly how the reference runs its loss (autograd)."""
+    from oracle import jsd_oracle as orc
+    fl = f.detach().clone().requires_grad_(True)
+    gl = g.detach().clone().requires_grad_(True)
+    tt = torch.tensor(t, dtype=torch.float32, requires_grad=True)
+    out = orc.jsd_dense(fl, gl, tt, row_offset=row_offset)
+    out["loss"].backward()
+    return float(out["loss"])
+
+
+def time_cpu(batch, dim, budget_s, steps=None, warmup=1):
+    """Times the CPU restatement on a bounded sample: a row slab of `rows` image rows against all
+    `batch` text rows (work per row is constant, so pairs/s = rows / t is the whole-problem rate)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    f, g = synth(batch, dim)
+    f, g = f.float(), g.float()
+    rows = min(batch, 256)
+    cpu_dense_step(f[:rows], g, T_INIT)                      # first call pays one-off thread-pool start-up
+    t0 = time.perf_counter()
+    cpu_dense_step(f[:rows], g, T_INIT)
+    probe = max(time.perf_counter() - t0, 1e-4)
+    n_steps = steps if steps is not None else 3
+    per_step = budget_s / (n_steps + warmup)
+    rows = int(min(batch, max(64, rows * per_step / probe)))
+    rows = max(64, rows // 64 * 64)
+    for _ in range(warmup):
+        cpu_dense_step(f[:rows], g, T_INIT)
+    times = []
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        cpu_dense_step(f[:rows], g, T_INIT)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": rows / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"dense fwd+backward() of a {rows}x{batch} row slab, D={dim}, fp32 torch CPU, "
+                      f"{n_steps} steps after {warmup} warm-up (mean {mean*1e3:.1f} ms/step)"}, mean, rows
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch, dim = wl["batch"] * (args.gpus if wl["weak"] else 1), wl["dim"]
+    base, mean, rows = time_cpu(batch, dim, budget_s=150.0, steps=args.steps, warmup=max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "neg_mode": "dense",
+                   "sample_rows": rows, "device": "host CPU"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200(args, wl):
+    import torch.distributed as dist
+    from clip_lite_b200 import kernels as K
+    from clip_lite_b200 import ops, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    batch = wl["batch"] * (world if wl["weak"] else 1)
+    dim = wl["dim"]
+    if batch % world:
+        raise SystemExit("global batch must divide by the number of GPUs")
+    rows = batch // world
+    f_all, g_all = synth(batch, dim)
+    f_host = f_all[rank * rows:(rank + 1) * rows].contiguous().pin_memory()
+    g_host = g_all[rank * rows:(rank + 1) * rows].contiguous().pin_memory()
+    f_dev = f_host.to(dev).requires_grad_(True)
+    g_dev = g_host.to(dev).requires_grad_(True)
+    t_dev = torch.tensor(T_INIT, device=dev, requires_grad=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def loss_fn(f, g):
+        if world > 1:
+            return parallel.gathered_dense_loss(f, g, t_dev)[0]
+        return ops.jsd_dense_loss(f, g, t_dev)[0]
+
+    def step():
+        loss = loss_fn(f_dev, g_dev)
+        return (loss,) + torch.autograd.grad(loss, (f_dev, g_dev, t_dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, flush_l2=True):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            if flush_l2:
+                flush.zero_()
+            starts[i].record()
+            fn()
+            ends[i].record()
+        barrier()
+        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        tt = torch.tensor(total_ms, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    loss_value = float(out[0])
+
+    with ClockSampler(local_rank) as clocks:
+        total_ms = timed(step, args.steps)
+    ms_per_step = total_ms / args.steps
+    value = batch / (ms_per_step * 1e-3)
+
+    # ---- end to end through host buffers (pinned): H2D inputs, fwd+bwd, D2H loss + gradients
+    df_host = torch.empty_like(f_host).pin_memory()
+    dg_host = torch.empty_like(g_host).pin_memory()
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        f = f_host.to(dev, non_blocking=True).requires_grad_(True)
+        g = g_host.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_fn(f, g)
+        gf, gg, _ = torch.autograd.grad(loss, (f, g, t_dev))
+        df_host.copy_(gf, non_blocking=True)
+        dg_host.copy_(gg, non_blocking=True)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    e2e_steps = max(5, min(args.steps, 50))
+    e2e_ms = timed(e2e_step, e2e_steps, flush_l2=False) / e2e_steps
+    e2e = {"value": batch / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": 2 * rows * dim * 2, "d2h_bytes_per_step": 2 * rows * dim * 2 + 4}
+
+    # ---- roofline of the dominant kernel family (the three tcgen05 GEMM launches of a step),
+    # timed live with CUDA events around each launch on the launching stream
+    peak_tf, peak_gbs, peak_src = load_peaks()
+    with torch.no_grad():
+        u, ut, inv_f = K.normalize_cast(f_dev.detach(), transpose=True)
+        v, _, inv_g = K.normalize_cast(g_dev.detach(), transpose=False)
+        if world > 1:
+            v_all = torch.empty(batch, dim, dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(v_all, v)
+        else:
+            v_all = v
+        vt_all = K.transpose_bf16(v_all)
+        gamma = torch.ones((), device=dev)
+        t_c = t_dev.detach()
+        _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
+        stages = {
+            "fwd": lambda: K.dense_fwd(u, v_all, t_c, row_offset=rank * rows),
+            "bwd_du": lambda: K.dense_bwd_du(gmat, vt_all, batch, t_c, gamma),
+            "bwd_dv": lambda: K.dense_bwd_dv(gmat, ut, batch, t_c, gamma),
+        }
+        stage_ms = {}
+        n_meas = max(5, min(args.steps, 50))
+        for name, fn in stages.items():
+            for _ in range(3):
+                fn()
+            stage_ms[name] = timed(fn, n_meas) / n_meas
+    flops_per_launch = 2.0 * rows * batch * dim                       # S = U V^T, dU = G V, dV = G^T U
+    gemm_ms = sum(stage_ms.values())
+    achieved = 3 * flops_per_launch / (gemm_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload if world == 1 else "", None)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "jsd_gemm_kernel (tcgen05, 3 launches/step: fwd, dU, dV)",
+                "algorithmic_flops_per_launch": flops_per_launch,
+                "launch_ms": stage_ms,
+                "step_frac_of_peak": 3 * flops_per_launch / (ms_per_step * 1e-3) / 1e12 / peak_tf}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _, _ = time_cpu(batch, dim, budget_s=20.0)
+        launches_per_step = 10 if world == 1 else 9    # normalize(+transpose) x2, fwd+finalize, dU, dV, normalize_bwd x2
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "rows_per_gpu": rows,
+                       "neg_mode": "dense", "parallelism": f"dp{world}",
+                       "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
+                       "inputs": "bf16 unit rows resident in HBM; N(0,1) features, text = 0.6 img + 0.8 noise"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
+            "tflops_6B2D": 6.0 * rows * batch * dim / (ms_per_step * 1e-3) / 1e12,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="dense_b8192_d1024")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -263,7 +263,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (is_diag) {
                   // positive pair: softplus(-x) = softplus(x) - x, dL/dx ~ -sigma(-x) = sigma(x) - 1
                   const float gneg = x >= 0.f ? -(e * rr) : -rr;   // -(1 - sigma(x)) without cancellation
-                  pos_sum += sp - x;
+                  pos_sum += fmaxf(-x, 0.f) + log1pf(e);           // rare path: full-precision softplus(-x)
                   dtp_sum = fmaf(gneg, x, dtp_sum);
                   p.gdiag[grow] = gneg;
                   sg[h] = 0.f;

@@ -1,0 +1,300 @@
+"""Drop-in replacement for the reference's ``loss.py`` module (CLIP-Lite).
+
+Same classes, constructor arguments, forward signature, sub-module names and
+``state_dict`` keys as the reference (loss.py:12-314), so model.py:94-101,
+factories.py:374-400, the checkpoint loader and the eval scripts that reach into
+``loss.global_d.img_block`` / ``text_block`` keep working unchanged.  What differs
+is where the estimator runs:
+
+* the projection heads (``MILinearBlock``) and the prior discriminators stay
+  PyTorch modules (cuBLAS/cuDNN), but each head runs ONCE per step: the
+  reference's second pass over the rolled text batch (loss.py:214-222) is a row
+  permutation of the first, so its negatives are indexed instead of re-projected;
+  the second BatchNorm running-statistics update that pass performed is replayed
+  exactly (``_forward_block_twice``);
+* normalise -> row dot * exp(t) -> softplus -> mean and the whole backward of
+  loss.py:94-105,204-254 run in libjsd_b200.so (``ops.jsd_index_loss``);
+* ``neg_mode="dense"`` switches to the all-pairs estimator on tcgen05 tensor
+  cores (``ops.jsd_dense_loss``), ``gather=True`` additionally all-gathers the
+  text embeddings across the data-parallel group (``parallel.gathered_dense_loss``).
+  Both default to the reference's behaviour (one rolled negative, per-rank loss).
+
+There is no CPU path: calling forward without CUDA tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+_DOT_TYPES = ("dot", "dotcon")          # global_d is the dot critic
+_CONCAT_TYPES = ("concat", "condot")    # global_d is the concat critic (not on the hot path)
+
+
+class MILinearBlock(nn.Module):
+    """Projection head: Linear -> BN -> ReLU -> Linear, plus a linear shortcut
+    initialised as a noisy identity, then LayerNorm (reference loss.py:12-40)."""
+
+    def __init__(self, feature_sz: int, units: int = 2048, bln: bool = True):
+        super().__init__()
+        self.feature_nonlinear = nn.Sequential(
+            nn.Linear(feature_sz, units, bias=False),
+            nn.BatchNorm1d(units),
+            nn.ReLU(),
+            nn.Linear(units, units),
+        )
+        self.feature_shortcut = nn.Linear(feature_sz, units)
+        self.feature_block_ln = nn.LayerNorm(units)
+        with torch.no_grad():
+            w = self.feature_shortcut.weight
+            w.uniform_(-0.01, 0.01)
+            k = min(units, feature_sz)
+            w[torch.arange(k), torch.arange(k)] = 1.0
+        self.bln = bln
+
+    def forward(self, feat: torch.Tensor) -> torch.Tensor:
+        out = self.feature_nonlinear(feat) + self.feature_shortcut(feat)
+        return self.feature_block_ln(out) if self.bln else out
+
+
+class PriorDiscriminator(nn.Module):
+    """3-layer MLP with sigmoid output for the uniform-prior matching term (loss.py:43-53)."""
+
+    def __init__(self, sz: int):
+        super().__init__()
+        self.l0 = nn.Linear(sz, 1000)
+        self.l1 = nn.Linear(1000, 200)
+        self.l2 = nn.Linear(200, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.sigmoid(self.l2(F.relu(self.l1(F.relu(self.l0(x))))))
+
+
+class GlobalDiscriminator(nn.Module):
+    """Concat critic (loss.py:56-68).  Not a dot-product score, hence outside the
+    tensor-core path; kept in PyTorch so that type="concat"/"condot"/"dotcon" modules
+    and their checkpoints still load and run."""
+
+    def __init__(self, sz: int):
+        super().__init__()
+        self.l0 = nn.Linear(sz, 512)
+        self.l1 = nn.Linear(512, 512)
+        self.l2 = nn.Linear(512, 1)
+
+    def forward(self, features1: torch.Tensor, features2: torch.Tensor) -> torch.Tensor:
+        h = F.relu(self.l0(torch.cat((features1, features2), dim=1)))
+        return self.l2(F.relu(self.l1(h)))
+
+
+class GlobalDiscriminatorDot(nn.Module):
+    """Dot critic (loss.py:76-107): two projection heads and a learnable log-temperature."""
+
+    def __init__(self, image_sz: int, text_sz: int, units: int = 2048, bln: bool = True):
+        super().__init__()
+        self.img_block = MILinearBlock(image_sz, units=units, bln=bln)
+        self.text_block = MILinearBlock(text_sz, units=units, bln=bln)
+        self.temperature = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+
+    def forward(self, features1: torch.Tensor = None, features2: torch.Tensor = None) -> torch.Tensor:
+        """Row-wise scores exp(t) * <u_n, v_n> as the reference returns them.  Only a
+        convenience for external callers; the loss below never takes this route."""
+        u = F.normalize(self.img_block(features1), p=2, dim=-1)
+        v = F.normalize(self.text_block(features2), p=2, dim=-1)
+        return (u * v).sum(-1) * self.temperature.exp()
+
+
+def _forward_block_twice(block: MILinearBlock, x: torch.Tensor) -> torch.Tensor:
+    """Run a projection head once while leaving its BatchNorm buffers exactly as
+    the reference's two passes (positives, then the permuted negatives) leave
+    them: both passes see the same batch statistics s, so after the first
+    update r1 = (1-m) r0 + m s the second is r2 = (2-m) r1 - (1-m) r0."""
+    bn = block.feature_nonlinear[1] if isinstance(block, MILinearBlock) else None
+    replay = block.training and isinstance(bn, nn.BatchNorm1d) and bn.track_running_stats \
+        and bn.running_mean is not None
+    if not replay:
+        return block(x)
+    mean0, var0 = bn.running_mean.clone(), bn.running_var.clone()
+    out = block(x)
+    with torch.no_grad():
+        if bn.momentum is None:                       # cumulative average: factor 1/n
+            n1 = bn.num_batches_tracked.to(mean0.dtype)
+            for buf, old in ((bn.running_mean, mean0), (bn.running_var, var0)):
+                stat = old + (buf - old) * n1
+                buf.add_((stat - buf) / (n1 + 1))
+        else:
+            m = bn.momentum
+            bn.running_mean.mul_(2.0 - m).sub_(mean0, alpha=1.0 - m)
+            bn.running_var.mul_(2.0 - m).sub_(var0, alpha=1.0 - m)
+        bn.num_batches_tracked.add_(1)
+    return out
+
+
+def _roll_minus_one(x: torch.Tensor) -> torch.Tensor:
+    return torch.cat((x[1:], x[:1]), dim=0)
+
+
+class JSDInfoMaxLoss(nn.Module):
+    """Jensen-Shannon mutual-information loss of CLIP-Lite behind the reference's
+    interface (loss.py:110-314).
+
+    Extra keyword-only options (defaults reproduce the reference):
+      neg_mode  "shift1": one negative per row, the text batch rolled by one
+                (reference semantics, HBM-bound fused kernel);
+                "dense": every off-diagonal pair is a negative (tensor-core kernels).
+      gather    with neg_mode="dense": all-gather the text embeddings over
+                ``process_group`` so that each rank scores its rows against the
+                global batch (gradients of the text side are reduce-scattered back).
+    """
+
+    def __init__(
+        self,
+        image_dim: int = 2048,
+        text_dim: int = 768,
+        type: str = "dot",
+        prior_weight: float = 0.1,
+        image_prior: bool = True,
+        text_prior: bool = False,
+        visual_self_supervised: bool = False,
+        textual_self_supervised: bool = False,
+        *,
+        neg_mode: str = "shift1",
+        gather: bool = False,
+        process_group=None,
+    ):
+        super().__init__()
+        if type not in _DOT_TYPES + _CONCAT_TYPES:
+            raise ValueError(f"unknown critic type {type!r}; expected one of {_DOT_TYPES + _CONCAT_TYPES}")
+        if neg_mode not in ("shift1", "dense"):
+            raise ValueError(f"neg_mode must be 'shift1' or 'dense', got {neg_mode!r}")
+        if gather and neg_mode != "dense":
+            raise ValueError("gather=True requires neg_mode='dense'")
+        if neg_mode == "dense" and type not in _DOT_TYPES:
+            raise ValueError("neg_mode='dense' needs the dot critic (type='dot' or 'dotcon')")
+        self.prior_weight = prior_weight
+        self.image_prior = image_prior
+        self.text_prior = text_prior
+        self.neg_mode = neg_mode
+        self.gather = gather
+        self.process_group = process_group
+
+        self.global_d = (GlobalDiscriminatorDot(image_sz=image_dim, text_sz=text_dim) if type in _DOT_TYPES
+                         else GlobalDiscriminator(sz=image_dim + text_dim))
+        ssl_dot = type in ("dot", "condot")       # which critic the SSL terms use (loss.py:129-169)
+        if visual_self_supervised:
+            self.visual_d = (GlobalDiscriminatorDot(image_sz=image_dim, text_sz=image_dim) if ssl_dot
+                             else GlobalDiscriminator(sz=image_dim + image_dim))
+        if textual_self_supervised:
+            self.textual_d = (GlobalDiscriminatorDot(image_sz=text_dim, text_sz=text_dim) if ssl_dot
+                              else GlobalDiscriminator(sz=text_dim + text_dim))
+        if self.image_prior:
+            self.prior_d = PriorDiscriminator(sz=image_dim)
+        if self.text_prior:
+            self.text_prior_d = PriorDiscriminator(sz=text_dim)
+        self._cluster_index: Dict[int, ops.NegativeIndex] = {}
+
+    # ------------------------------------------------------------------ pieces
+    def prior_terms(self, image_features: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
+        """Adversarial uniform-prior matching (loss.py:186-200).  Plain PyTorch: RNG-dependent,
+        tiny, and outside the hot path."""
+        prior = torch.zeros((), device=image_features.device)
+        if self.image_prior:
+            noise = torch.rand_like(image_features)
+            prior = prior - (torch.log(self.prior_d(noise)).mean()
+                             + torch.log(1.0 - self.prior_d(image_features)).mean())
+        if self.text_prior:
+            noise = torch.rand_like(text_features)
+            prior = prior - (torch.log(self.text_prior_d(noise)).mean()
+                             + torch.log(1.0 - self.text_prior_d(text_features)).mean())
+        return prior
+
+    def _cluster_neg_index(self, half: int) -> ops.NegativeIndex:
+        if half not in self._cluster_index:
+            self._cluster_index[half] = ops.NegativeIndex.cluster(half)
+        return self._cluster_index[half]
+
+    def _estimate(self, critic: nn.Module, feats1: torch.Tensor, feats2: torch.Tensor,
+                  neg_index: Optional[ops.NegativeIndex], allow_dense: bool) -> torch.Tensor:
+        """Em - Ej for one critic (the body shared by loss.py:204-254, :257-277, :280-300)."""
+        if isinstance(critic, GlobalDiscriminatorDot):
+            f = _forward_block_twice(critic.img_block, feats1)
+            g = _forward_block_twice(critic.text_block, feats2)
+            if allow_dense and self.neg_mode == "dense":
+                if self.gather:
+                    from . import parallel
+                    loss, _ = parallel.gathered_dense_loss(f, g, critic.temperature, self.process_group)
+                else:
+                    loss, _ = ops.jsd_dense_loss(f, g, critic.temperature)
+            else:
+                loss, _ = ops.jsd_index_loss(f, g, critic.temperature, neg_index)
+            return loss
+        # concat critic: two passes, as in the reference (not the accelerated path)
+        if neg_index is None:
+            feats2_neg = _roll_minus_one(feats2)
+        else:
+            feats2_neg = feats2[neg_index.on(feats2.device)[0].long()]
+        ej = -F.softplus(-critic(feats1, feats2)).mean()
+        em = F.softplus(critic(feats1, feats2_neg)).mean()
+        return em - ej
+
+    # ------------------------------------------------------------------ forward
+    def forward(
+        self,
+        image_features: torch.Tensor,
+        text_features: torch.Tensor,
+        neg_image_features: Optional[torch.Tensor] = None,
+        neg_text_features: Optional[torch.Tensor] = None,
+        aug_image_features: Optional[torch.Tensor] = None,
+        aug_text_features: Optional[torch.Tensor] = None,
+    ) -> Dict[str, torch.Tensor]:
+        if not image_features.is_cuda:
+            raise RuntimeError("JSDInfoMaxLoss (B200) needs CUDA tensors; there is no CPU path")
+        if image_features.shape[0] != text_features.shape[0]:
+            raise ValueError("image and text batches differ in size")
+        device = image_features.device
+        prior = self.prior_terms(image_features, text_features)
+
+        if neg_text_features is None:
+            cross = self._estimate(self.global_d, image_features, text_features, None, allow_dense=True)
+        else:
+            if neg_image_features is None:
+                raise ValueError("cluster mode needs neg_image_features together with neg_text_features")
+            half = image_features.shape[0]
+            images_all = torch.cat((image_features, neg_image_features), dim=0)
+            texts_all = torch.cat((text_features, neg_text_features), dim=0)
+            cross = self._estimate(self.global_d, images_all, texts_all, self._cluster_neg_index(half),
+                                   allow_dense=True)
+            # the reference re-binds text_features to its rolled copy here (loss.py:237-239),
+            # which the textual self-supervised term below then sees
+            text_features = _roll_minus_one(text_features)
+
+        visual = torch.zeros((), device=device)
+        if aug_image_features is not None:
+            visual = self._estimate(self.visual_d, image_features, aug_image_features, None, allow_dense=False)
+        textual = torch.zeros((), device=device)
+        if aug_text_features is not None:
+            textual = self._estimate(self.textual_d, text_features, aug_text_features, None, allow_dense=False)
+
+        jsd = cross + visual + textual
+        total = (1.0 - self.prior_weight) * jsd + self.prior_weight * prior
+        return {
+            "total_loss": total,
+            "cross_modal_loss": cross,
+            "visual_loss": visual,
+            "textual_loss": textual,
+        }
+
+
+def register_with_reference(factories_module=None, loss_module=None) -> None:
+    """Swap this class into an imported reference tree: ``LossFactory.PRODUCTS["jsd"]``
+    (factories.py:374-376) and ``loss.JSDInfoMaxLoss`` (imported by model.py:11)."""
+    if factories_module is not None:
+        factories_module.LossFactory.PRODUCTS["jsd"] = JSDInfoMaxLoss
+        if hasattr(factories_module, "JSDInfoMaxLoss"):
+            factories_module.JSDInfoMaxLoss = JSDInfoMaxLoss
+    if loss_module is not None:
+        loss_module.JSDInfoMaxLoss = JSDInfoMaxLoss

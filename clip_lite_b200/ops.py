@@ -1,0 +1,133 @@
+"""Autograd entry points of the JSD estimator.  Each Function only moves tensors
+in and out of the C ABI (clip_lite_b200.kernels); the arithmetic of
+loss.py:94-105,204-254 and of its backward runs in libjsd_b200.so.
+
+    jsd_index_loss(f, g, t, neg_index=None)   reference semantics: one indexed negative per row
+    jsd_dense_loss(f, g, t)                   all off-diagonal pairs as negatives (single GPU)
+
+f, g are the projected features ([B, D]; fp32, bf16 or fp16), t the 0-dim
+`temperature` parameter.  Both return (loss, stats) where loss is the 0-dim
+CROSS_MODAL_LOSS = Em - Ej of loss.py:254 and stats = [pos, neg, loss, dL/dt]
+(detached, for logging without a host sync).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import kernels as K
+
+
+class NegativeIndex:
+    """Device-side negative index of the index mode together with its CSR inverse.
+
+    The reference builds its negatives by concatenating / rolling tensors
+    (loss.py:214-216 normal mode, loss.py:225-252 cluster mode); here the same
+    pairing is an index vector so that the projection heads run once.
+    """
+
+    def __init__(self, neg_index: torch.Tensor):
+        if neg_index.dim() != 1:
+            raise ValueError("neg_index must be 1-D")
+        n = neg_index.numel()
+        idx = neg_index.detach().to(torch.int64).cpu()
+        if n == 0 or int(idx.min()) < 0 or int(idx.max()) >= n:
+            raise ValueError("neg_index entries must lie in [0, B)")
+        order = torch.argsort(idx, stable=True)
+        ptr = torch.zeros(n + 1, dtype=torch.int64)
+        ptr[1:] = torch.cumsum(torch.bincount(idx, minlength=n), 0)
+        self.n = n
+        self._host = (idx.to(torch.int32), ptr.to(torch.int32), order.to(torch.int32))
+        self._dev = {}
+
+    def on(self, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = tuple(x.to(device) for x in self._host)
+        return self._dev[key]
+
+    @staticmethod
+    def cluster(half: int) -> "NegativeIndex":
+        """Row i < half -> half + i (its hard negative), row half + i -> (i + 1) mod half."""
+        i = torch.arange(half)
+        return NegativeIndex(torch.cat((half + i, (i + 1) % half)))
+
+
+def _common(f: torch.Tensor, g: torch.Tensor):
+    if f.dim() != 2 or g.dim() != 2:
+        raise ValueError(f"features must be [B, D]; got {tuple(f.shape)} and {tuple(g.shape)}")
+    if f.shape != g.shape:
+        raise ValueError(f"image features {tuple(f.shape)} and text features {tuple(g.shape)} must match after projection")
+    if not (f.is_cuda and g.is_cuda):
+        raise RuntimeError("the JSD estimator runs on CUDA only (no CPU fallback)")
+    dt = torch.promote_types(f.dtype, g.dtype)
+    if dt not in (torch.float32, torch.bfloat16, torch.float16):
+        dt = torch.float32
+    return f.to(dt).contiguous(), g.to(dt).contiguous()
+
+
+class _JSDIndexFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, g, t, neg: Optional[NegativeIndex]):
+        with torch.autocast("cuda", enabled=False):
+            fc, gc = _common(f, g)
+            if neg is not None and neg.n != fc.shape[0]:
+                raise ValueError(f"neg_index has {neg.n} entries for a batch of {fc.shape[0]}")
+            ix = neg.on(fc.device) if neg is not None else (None, None, None)
+            out4, df, dg = K.index_fwd_bwd(fc, gc, t, *ix)
+        ctx.save_for_backward(df, dg, out4)
+        ctx.dtypes = (f.dtype, g.dtype, t.dtype)
+        stats = out4.clone()
+        ctx.mark_non_differentiable(stats)
+        return out4[2].clone(), stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        df, dg, out4 = ctx.saved_tensors
+        go = grad_loss.float()
+        fd, gd, td = ctx.dtypes
+        return (go * df).to(fd), (go * dg).to(gd), (go * out4[3]).to(td), None
+
+
+class _JSDDenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, g, t):
+        need_grad = any(ctx.needs_input_grad)
+        with torch.autocast("cuda", enabled=False):
+            fc, gc = _common(f, g)
+            u, ut, inv_f = K.normalize_cast(fc, transpose=need_grad)
+            v, vt, inv_g = K.normalize_cast(gc, transpose=need_grad)
+            out4, gmat, gdiag = K.dense_fwd(u, v, t, row_offset=0, want_grad=need_grad)
+        if need_grad:
+            ctx.save_for_backward(fc, gc, t, u, v, ut, vt, inv_f, inv_g, gmat, gdiag, out4)
+        ctx.dtypes = (f.dtype, g.dtype, t.dtype)
+        stats = out4.clone()
+        ctx.mark_non_differentiable(stats)
+        return out4[2].clone(), stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        fc, gc, t, u, v, ut, vt, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
+        b = fc.shape[0]
+        with torch.autocast("cuda", enabled=False):
+            gamma = grad_loss.float()
+            du = K.dense_bwd_du(gmat, vt, b, t, gamma)
+            dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+            df = K.normalize_bwd(fc, inv_f, du, v, 0, gdiag, t, gamma, b)
+            dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, b)
+        fd, gd, td = ctx.dtypes
+        return df.to(fd), dg.to(gd), (gamma * out4[3]).to(td)
+
+
+def jsd_index_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[NegativeIndex] = None):
+    """Reference estimator (loss.py:204-254): negatives = text rows rolled by one,
+    or the rows named by ``neg_index``."""
+    return _JSDIndexFn.apply(f, g, t, neg_index)
+
+
+def jsd_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor):
+    """All-pairs estimator: mean_i sp(-S_ii) + mean_{i != j} sp(S_ij) on tensor cores."""
+    if f.shape[0] < 2:
+        raise ValueError("the dense estimator needs at least two rows (one negative per row)")
+    return _JSDDenseFn.apply(f, g, t)

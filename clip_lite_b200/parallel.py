@@ -1,0 +1,105 @@
+"""Data-parallel dense estimator: each rank scores its rows against the global batch.
+
+Not in the reference (its loss is per-rank); this is the north-star
+path of BASELINE.json.  One process per GPU, ``torch.distributed`` (NCCL over
+NVLink/NVSwitch) for the two exchange steps the path really has:
+
+  forward   V_r --all-gather--> V_all [B, D] bf16; rank r computes the row slab
+            S_r = tau U_r V_all^T  (positives on column r*M + i) and its local
+            loss L_r; nothing else crosses ranks.
+  backward  dU_r = tau G_r V_all is complete locally;  dV_all^(r) = tau G_r^T U_r is
+            a partial over all text rows --reduce-scatter(sum)--> dV_r.
+
+Gradient convention: every rank back-propagates its OWN slab loss
+L_r; the reduce-scatter sums the partials, so DDP's later mean over ranks of the
+parameter gradients yields the gradient of mean_r L_r, the global loss.
+
+All kernel work goes through ``clip_lite_b200.kernels`` (module attribute ``K``
+so that the CPU gloo tests can substitute an oracle-backed stand-in for the
+collective/sharding logic; the product never does).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+
+def _world(group) -> tuple:
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
+    out = torch.empty(world * x.shape[0], x.shape[1], dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
+    out = torch.empty(x.shape[0] // world, x.shape[1], dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+class _GatheredDenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, g, t, group):
+        rank, world = _world(group)
+        need_grad = any(ctx.needs_input_grad)
+        if f.dim() != 2 or f.shape != g.shape:
+            raise ValueError(f"features must both be [B_local, D]; got {tuple(f.shape)} and {tuple(g.shape)}")
+        m = f.shape[0]
+        with torch.autocast(f.device.type, enabled=False):
+            dt = torch.promote_types(f.dtype, g.dtype)
+            fc, gc = f.to(dt).contiguous(), g.to(dt).contiguous()
+            u, ut, inv_f = K.normalize_cast(fc, transpose=need_grad)
+            v, _, inv_g = K.normalize_cast(gc, transpose=False)
+            v_all = _all_gather_rows(v, world, group) if world > 1 else v
+            out4, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
+            vt_all = K.transpose_bf16(v_all) if need_grad else None
+        if need_grad:
+            ctx.save_for_backward(fc, gc, t, u, ut, v_all, vt_all, inv_f, inv_g, gmat, gdiag, out4)
+        ctx.group, ctx.rank, ctx.world = group, rank, world
+        ctx.dtypes = (f.dtype, g.dtype, t.dtype)
+        stats = out4.clone()
+        ctx.mark_non_differentiable(stats)
+        return out4[2].clone(), stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        fc, gc, t, u, ut, v_all, vt_all, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
+        m, n = fc.shape[0], v_all.shape[0]
+        with torch.autocast(fc.device.type, enabled=False):
+            gamma = grad_loss.float()
+            # text side first so that its reduce-scatter is in flight during the image side
+            dv_partial = K.dense_bwd_dv(gmat, ut, n, t, gamma)                 # [N, D], partial over ranks
+            dv = _reduce_scatter_rows(dv_partial, ctx.world, ctx.group) if ctx.world > 1 else dv_partial
+            du = K.dense_bwd_du(gmat, vt_all, n, t, gamma)                     # [M, D], complete
+            df = K.normalize_bwd(fc, inv_f, du, v_all, ctx.rank * m, gdiag, t, gamma, m)
+            dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, m)
+        fd, gd, td = ctx.dtypes
+        return df.to(fd), dg.to(gd), (gamma * out4[3]).to(td), None
+
+
+def gathered_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group: Optional[object] = None):
+    """(L_r, stats) for this rank's rows against the all-gathered text batch.
+    f, g: [B_local, D] projected features (same B_local on every rank)."""
+    _, world = _world(group)
+    if world * f.shape[0] < 2:
+        raise ValueError("the dense estimator needs at least two rows in the global batch")
+    return _GatheredDenseFn.apply(f, g, t, group)
+
+
+def global_loss_for_logging(local_loss: torch.Tensor, group: Optional[object] = None) -> torch.Tensor:
+    """mean_r L_r (detached): the value to log; never back-propagate it (see module docstring)."""
+    out = local_loss.detach().clone()
+    _, world = _world(group)
+    if world > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        out /= world
+    return out

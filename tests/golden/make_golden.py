@@ -50,9 +50,11 @@ def estimator_case(name, b, d, seed, correlated, t, mode="normal", ssl=False):
         for blk in (m.visual_d, m.textual_d):
             blk.img_block = torch.nn.Identity()
             blk.text_block = torch.nn.Identity()
-            blk.temperature.data.fill_(t - 0.3)
     m = m.double()
     m.global_d.temperature.data.fill_(t)
+    if ssl:
+        m.visual_d.temperature.data.fill_(t - 0.3)
+        m.textual_d.temperature.data.fill_(t - 0.3)
     inputs = {"image_features": f, "text_features": g}
     if mode == "cluster":
         nf, ng = synth_embeddings(b, d, seed + 100, correlated)

@@ -20,23 +20,23 @@ SIGNATURES = {
     "jsd_index_workspace_bytes": (c_size_t, [c_int64]),
     "jsd_index_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "jsd_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
-                                   c_void_p]),
-    "jsd_transpose_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "jsd_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "jsd_dense_workspace_bytes": (c_size_t, []),
     "jsd_dense_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
-    "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+    "jsd_streamk_workspace_bytes": (c_size_t, []),
+    "jsd_streamk_flag_bytes": (c_size_t, []),
+    "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
-    "jsd_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+    "jsd_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_bwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
-    "jsd_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
-                              c_void_p]),
+    "jsd_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64,
+                              c_void_p, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 

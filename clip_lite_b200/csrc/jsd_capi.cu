@@ -67,6 +67,8 @@ int make_tmap(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int
   return 0;
 }
 
+size_t streamk_flag_bytes() { return (size_t)jsd::SK_MAX_CTAS * jsd::NUM_EPI_WARPS * sizeof(int); }
+
 int sm_count_cached() {
   static int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -78,10 +80,10 @@ int sm_count_cached() {
   return cached;
 }
 
-template <int MODE, bool A_MN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const jsd::GemmParams& p, cudaStream_t st,
-                int* grid_out = nullptr) {
-  auto kern = jsd::jsd_gemm_kernel<MODE, A_MN>;
+template <int MODE, bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams p, void* sk_workspace,
+                cudaStream_t st, int* grid_out = nullptr) {
+  auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, jsd::GEMM_SMEM_BYTES));
@@ -91,11 +93,29 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const jsd::GemmP
   JSD_REQUIRE(sms > 0, "no CUDA device");
   const long long tiles = (long long)((p.M + jsd::BLOCK_M - 1) / jsd::BLOCK_M) *
                           ((p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N);
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  int grid = (int)(tiles < sms ? tiles : sms);
+  // stream-K pays when whole tiles leave part of the last wave idle (e.g. 256 tiles on 148 SMs)
+  p.stream_k = 0;
+  if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && tiles > sms && tiles % sms != 0 &&
+      sms <= jsd::SK_MAX_CTAS) {
+    p.stream_k = 1;
+    p.sk_flags = reinterpret_cast<int*>(sk_workspace);
+    p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
+    grid = sms;
+  }
   if (grid_out) *grid_out = grid;
   kern<<<grid, jsd::GEMM_THREADS, jsd::GEMM_SMEM_BYTES, st>>>(tmA, tmB, p);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int MODE>
+int launch_gemm_any(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const jsd::GemmParams& p,
+                    void* sk_workspace, cudaStream_t st) {
+  if (a_mn) return b_mn ? launch_gemm<MODE, true, true>(tmA, tmB, p, sk_workspace, st)
+                        : launch_gemm<MODE, true, false>(tmA, tmB, p, sk_workspace, st);
+  return b_mn ? launch_gemm<MODE, false, true>(tmA, tmB, p, sk_workspace, st)
+              : launch_gemm<MODE, false, false>(tmA, tmB, p, sk_workspace, st);
 }
 
 bool fits_int(int64_t v) { return v > 0 && v < (int64_t)1 << 30; }
@@ -163,7 +183,7 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
 
 extern "C" {
 
-int jsd_abi_version(void) { return 1; }
+int jsd_abi_version(void) { return 2; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -191,27 +211,13 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
   return 0;
 }
 
-int jsd_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn, float* inv_norm,
                        jsd_stream_t stream) {
-  JSD_REQUIRE(in && out, "jsd_transpose_bf16: null pointer argument");
-  JSD_REQUIRE(fits_int(rows) && fits_int(cols) && ld_in >= cols && ld_out >= rows, "jsd_transpose_bf16: bad shape");
-  dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
-  jsd::transpose_bf16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in, (int)rows, (int)cols, ld_in, (__nv_bfloat16*)out, ld_out);
-  JSD_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn, void* XnT, int64_t ldt,
-                       float* inv_norm, jsd_stream_t stream) {
   JSD_REQUIRE(X && Xn && inv_norm, "jsd_normalize_cast: null pointer argument");
   JSD_REQUIRE(fits_int(rows) && fits_int(D), "jsd_normalize_cast: rows=%lld, D=%lld out of range", (long long)rows,
               (long long)D);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = [&]() -> int { JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(X, rows, D, Xn, inv_norm, st))); }();
-  if (rc) return rc;
-  if (XnT) return jsd_transpose_bf16(Xn, rows, D, D, XnT, ldt, stream);
-  return 0;
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(X, rows, D, Xn, inv_norm, st)));
 }
 
 size_t jsd_dense_workspace_bytes(void) {
@@ -247,7 +253,7 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   p.partials = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = 0;
-  if (int rc = launch_gemm<jsd::MODE_FWD, false>(tmA, tmB, p, st, &grid)) return rc;
+  if (int rc = launch_gemm<jsd::MODE_FWD, false, false>(tmA, tmB, p, nullptr, st, &grid)) return rc;
   const double inv_pos = 1.0 / (double)M;
   const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
   jsd::finalize_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS,
@@ -256,25 +262,29 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   return 0;
 }
 
-static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* XT, int64_t ldxt, int64_t M,
-                            int64_t N, int64_t D, const float* t_dev, const float* gamma_dev, float* out,
+size_t jsd_streamk_flag_bytes(void) { return streamk_flag_bytes(); }
+
+size_t jsd_streamk_workspace_bytes(void) {
+  return streamk_flag_bytes() + (size_t)jsd::SK_MAX_CTAS * jsd::SK_SLOT_FLOATS * sizeof(float);
+}
+
+static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* X, int64_t M, int64_t N, int64_t D,
+                            const float* t_dev, const float* gamma_dev, void* sk_workspace, float* out,
                             jsd_stream_t stream) {
-  JSD_REQUIRE(Gmat && XT && t_dev && out, "jsd_dense_bwd: null pointer argument");
+  JSD_REQUIRE(Gmat && X && t_dev && out, "jsd_dense_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_bwd: M=%lld N=%lld D=%lld out of range",
               (long long)M, (long long)N, (long long)D);
-  JSD_REQUIRE(D % 4 == 0, "jsd_dense_bwd: D must be a multiple of 4");
+  JSD_REQUIRE(D % 8 == 0, "jsd_dense_bwd: D must be a multiple of 8");
   JSD_REQUIRE(ldg >= N && ldg % 8 == 0, "jsd_dense_bwd: bad ldg");
-  const int64_t kdim = dv ? M : N;     // contraction length
+  const int64_t kdim = dv ? M : N;     // contraction length = rows of the bf16 operand X
   const int64_t rows = dv ? N : M;     // rows of the gradient
-  JSD_REQUIRE(ldxt >= kdim && ldxt % 8 == 0, "jsd_dense_bwd: transposed operand pitch must be >= %lld and a multiple of 8",
-              (long long)kdim);
   CUtensorMap tmA, tmB;
   if (!dv) {
-    if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;   // [M, N], K = N
+    if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;   // [M, N] K-major, K = N
   } else {
-    if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, 64, jsd::BLOCK_K)) return rc;             // MN-major: box 64 j x 64 i
+    if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, 64, jsd::BLOCK_K)) return rc;             // MN-major: 64 j x 64 i boxes
   }
-  if (int rc = make_tmap(&tmB, XT, kdim, D, ldxt, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;    // [D, kdim]
+  if (int rc = make_tmap(&tmB, X, D, kdim, D, 64, jsd::BLOCK_K)) return rc;                  // [kdim, D] MN-major boxes
   jsd::GemmParams p{};
   p.M = (int)rows;
   p.N = (int)D;
@@ -285,18 +295,19 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
   p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;
   p.out = out;
   p.ldo = D;
-  cudaStream_t st = (cudaStream_t)stream;
-  return dv ? launch_gemm<jsd::MODE_GRAD, true>(tmA, tmB, p, st) : launch_gemm<jsd::MODE_GRAD, false>(tmA, tmB, p, st);
+  return launch_gemm_any<jsd::MODE_GRAD>(dv, true, tmA, tmB, p, sk_workspace, (cudaStream_t)stream);
 }
 
-int jsd_dense_bwd_du(const void* Gmat, int64_t ldg, const void* VT, int64_t ldvt, int64_t M, int64_t N, int64_t D,
-                     const float* t_dev, const float* gamma_dev, float* dUacc, jsd_stream_t stream) {
-  return dense_bwd_common(false, Gmat, ldg, VT, ldvt, M, N, D, t_dev, gamma_dev, dUacc, stream);
+int jsd_dense_bwd_du(const void* Gmat, int64_t ldg, const void* V, int64_t M, int64_t N, int64_t D,
+                     const float* t_dev, const float* gamma_dev, void* sk_workspace, float* dUacc,
+                     jsd_stream_t stream) {
+  return dense_bwd_common(false, Gmat, ldg, V, M, N, D, t_dev, gamma_dev, sk_workspace, dUacc, stream);
 }
 
-int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* UT, int64_t ldut, int64_t M, int64_t N, int64_t D,
-                     const float* t_dev, const float* gamma_dev, float* dVacc, jsd_stream_t stream) {
-  return dense_bwd_common(true, Gmat, ldg, UT, ldut, M, N, D, t_dev, gamma_dev, dVacc, stream);
+int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, int64_t M, int64_t N, int64_t D,
+                     const float* t_dev, const float* gamma_dev, void* sk_workspace, float* dVacc,
+                     jsd_stream_t stream) {
+  return dense_bwd_common(true, Gmat, ldg, U, M, N, D, t_dev, gamma_dev, sk_workspace, dVacc, stream);
 }
 
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
@@ -310,8 +321,8 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
                                                      gamma_dev, inv_rows, dX, st)));
 }
 
-int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int64_t M, int64_t N,
-                  int64_t K, float* C, jsd_stream_t stream) {
+int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,
+                  int64_t N, int64_t K, void* sk_workspace, float* C, jsd_stream_t stream) {
   JSD_REQUIRE(A && B && C, "jsd_gemm_bf16: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(K), "jsd_gemm_bf16: bad shape");
   JSD_REQUIRE(N % 4 == 0, "jsd_gemm_bf16: N must be a multiple of 4");
@@ -321,7 +332,11 @@ int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
   } else {
     if (int rc = make_tmap(&tmA, A, K, M, lda, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;
   }
-  if (int rc = make_tmap(&tmB, B, K, N, ldb, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;
+  if (b_mn_major) {
+    if (int rc = make_tmap(&tmB, B, N, K, ldb, 64, jsd::BLOCK_K)) return rc;     // B^T stored [K, ldb]
+  } else {
+    if (int rc = make_tmap(&tmB, B, K, N, ldb, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;
+  }
   jsd::GemmParams p{};
   p.M = (int)M;
   p.N = (int)N;
@@ -332,9 +347,8 @@ int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
   p.scale = 1.f;
   p.out = C;
   p.ldo = N;
-  cudaStream_t st = (cudaStream_t)stream;
-  return a_mn_major ? launch_gemm<jsd::MODE_GRAD, true>(tmA, tmB, p, st)
-                    : launch_gemm<jsd::MODE_GRAD, false>(tmA, tmB, p, st);
+  return launch_gemm_any<jsd::MODE_GRAD>(a_mn_major != 0, b_mn_major != 0, tmA, tmB, p, sk_workspace,
+                                          (cudaStream_t)stream);
 }
 
 }  // extern "C"

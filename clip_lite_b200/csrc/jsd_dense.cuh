@@ -2,20 +2,27 @@
 //
 // One warp-specialised, persistent tcgen05 GEMM kernel, instantiated three ways:
 //
-//   FWD      S = U . V^T                       (A = U  [M,D]  K-major, B = V   [N,D] K-major)
+//   FWD      S = U . V^T                (A = U [M,D] K-major,      B = V [N,D] K-major)
 //            epilogue: x = tau*S -> softplus / sigmoid -> per-CTA loss partials,
-//            Gmat[i,j] = sigma(x_ij) (bf16, 0 on the positive diagonal), gdiag[i] = -sigma(-x_ii)
-//   GRAD_DU  dUacc = scale * Gmat . V          (A = Gmat [M,N] K-major, B = V^T [D,N] K-major)
-//   GRAD_DV  dVacc = scale * Gmat^T . U        (A = Gmat read MN-major,  B = U^T [D,M] K-major)
+//            Gmat[i,j] = sigma(x_ij) (bf16, 0 on the positives), gdiag[i] = -sigma(-x_ii')
+//   GRAD_DU  dUacc = scale * Gmat   . V (A = Gmat [M,N] K-major,   B = V [N,D] read MN-major)
+//   GRAD_DV  dVacc = scale * Gmat^T . U (A = Gmat read MN-major,   B = U [M,D] read MN-major)
 //
-// The B x B score matrix itself is never written; what crosses the fwd/bwd
-// boundary is the bf16 sigmoid-coefficient matrix Gmat (see DESIGN.md for why the
-// dU/dV accumulators of a D=1024 problem cannot live in TMEM next to S tiles).
+// The B x B score matrix itself is never written; what crosses the fwd/bwd boundary is
+// the bf16 sigmoid-coefficient matrix Gmat (DESIGN.md explains why the dU/dV accumulators
+// of a D=1024 problem cannot live in TMEM next to the S tiles).  No operand is ever
+// transposed in memory: the MN-major UMMA descriptors read U, V and Gmat as they lie.
 //
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
 // allocator, warps 4..11 = epilogue (two column halves x four TMEM lane quarters).
-// Pipelines: 4-stage smem ring (full/empty mbarriers), 2-stage TMEM accumulator
-// ring (tfull/tempty) so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Pipelines: 4-stage smem ring (full/empty mbarriers), 2-stage TMEM accumulator ring
+// (tfull/tempty) so the epilogue of one tile overlaps the MMAs of the next.
+//
+// Scheduling: FWD walks whole 128x256 tiles round-robin.  The GRAD GEMMs (256 tiles of
+// 128 k-chunks on 148 SMs at B=8192, D=1024 -> 1.73 waves) use stream-K: the
+// (tile, k-chunk) space is cut into one contiguous range per CTA; a CTA that ends up
+// with the tail of a tile publishes its fp32 partial accumulator to a workspace slot, the
+// CTA holding the head of that tile adds the partials in its epilogue.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -32,12 +39,15 @@ constexpr int ACC_STAGES = 2;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int MN_ATOM_BYTES = 64 * BLOCK_K * 2;       // one 64-wide MN-major atom: 64 k-rows x 128 B
 constexpr int NUM_CTRL_WARPS = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 32 * (NUM_CTRL_WARPS + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* align slack */ + 256 /* barriers */;
 constexpr int PARTIALS_PER_WARP = 4;                  // pos, neg, dt_pos, dt_neg
+constexpr int SK_SLOT_FLOATS = BLOCK_M * BLOCK_N;     // one fp32 partial accumulator tile
+constexpr int SK_MAX_CTAS = 256;                      // flags / slots reserved in the workspace
 
 enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1 };
 
@@ -45,7 +55,7 @@ struct GemmParams {
   int M;            // rows of the output tile space (FWD: image rows; GRAD: rows of the gradient)
   int N;            // cols of the output tile space (FWD: text rows;  GRAD: D)
   int K;            // contraction length
-  int n_fastest;    // tile order: 1 = consecutive CTAs walk N first (A tile shared through L2)
+  int n_fastest;    // tile order: 1 = consecutive tiles walk N first (A tile shared through L2)
   // FWD
   int row_offset;   // column of the positive of local row 0
   const float* t_dev;
@@ -58,9 +68,65 @@ struct GemmParams {
   float scale;             // 1 / (M_rows * (N_cols - 1))
   float* out;              // [M, N] fp32, pitch ldo
   long long ldo;
+  // stream-K (GRAD): sk_flags [SK_MAX_CTAS * NUM_EPI_WARPS] ints, zero between launches;
+  // sk_slots [grid * SK_SLOT_FLOATS] floats.  stream_k = 0 -> whole tiles, round-robin.
+  int stream_k;
+  int* sk_flags;
+  float* sk_slots;
 };
 
-template <int MODE, bool A_MN>
+// Score of a masked (out-of-range) pair: tau * kMaskedScore is finite and so negative that
+// softplus, sigmoid and sigmoid * x are exactly 0 in fp32.
+constexpr float kMaskedScore = -30000.f;
+
+// Negative-pair terms of one score s = <u_i, v_j>:  x = tau s,  sp = softplus(x),  sg = sigmoid(x).
+//   e = exp(-|x|) (MUFU.EX2), r = 1/(1+e) (MUFU.RCP), log1p(e) = e * q(e) with a degree-4 minimax
+//   q on [0, 1] (|error| < 1e-5, FMA pipe) -- two MUFU ops per element instead of three.
+__device__ __forceinline__ void neg_terms(float s, float tau, float tau_l2, float& sp, float& sg) {
+  const float x = s * tau;
+  const float e = ex2_approx(-fabsf(s * tau_l2));
+  const float rr = rcp_approx(1.f + e);
+  float q = fmaf(e, 0.032151564955711365f, -0.136042982339859f);
+  q = fmaf(e, q, 0.28945469856262207f);
+  q = fmaf(e, q, -0.49190056324005127f);
+  q = fmaf(e, q, 0.9994943737983704f);
+  sp = fmaf(e, q, fmaxf(x, 0.f));
+  sg = x >= 0.f ? rr : 1.f - rr;
+}
+
+// Work iterator shared by the three roles: yields (tile, k_begin, k_end) segments.
+struct SegmentIter {
+  int num_k, num_tiles, stride, tile;   // round-robin whole tiles
+  long long u, u_end;                   // stream-K unit range of this CTA
+  bool stream_k;
+  __device__ SegmentIter(bool sk, int cta, int grid, int tiles, int nk)
+      : num_k(nk), num_tiles(tiles), stride(grid), tile(cta), u(0), u_end(0), stream_k(sk) {
+    if (sk) {
+      const long long total = (long long)tiles * nk;
+      u = total * cta / grid;
+      u_end = total * (cta + 1) / grid;
+    }
+  }
+  __device__ bool next(int& t, int& k0, int& k1) {
+    if (stream_k) {
+      if (u >= u_end) return false;
+      t = (int)(u / num_k);
+      k0 = (int)(u - (long long)t * num_k);
+      const long long rem = u_end - u;
+      k1 = (k0 + rem < num_k) ? (int)(k0 + rem) : num_k;
+      u += k1 - k0;
+      return true;
+    }
+    if (tile >= num_tiles) return false;
+    t = tile;
+    k0 = 0;
+    k1 = num_k;
+    tile += stride;
+    return true;
+  }
+};
+
+template <int MODE, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -81,6 +147,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const bool stream_k = (MODE == MODE_GRAD) && p.stream_k != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -121,11 +188,13 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-        for (int kc = 0; kc < num_k; ++kc) {
+        for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
@@ -133,11 +202,18 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if constexpr (!A_MN) {
             tma_load_2d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m0);
           } else {
-            // A is stored [K, M] with M contiguous: two 64-wide MN atoms of 64 k-rows each
-            tma_load_2d(a_dst, &tmA, full_bar(stage), m0, kc * BLOCK_K);
-            tma_load_2d(a_dst + A_TILE_BYTES / 2, &tmA, full_bar(stage), m0 + 64, kc * BLOCK_K);
+            // A stored [K, M] with M contiguous: 64-wide MN atoms of 64 k-rows each
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              tma_load_2d(a_dst + a * MN_ATOM_BYTES, &tmA, full_bar(stage), m0 + 64 * a, kc * BLOCK_K);
           }
-          tma_load_2d(b_dst, &tmB, full_bar(stage), kc * BLOCK_K, n0);
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tmB, full_bar(stage), kc * BLOCK_K, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a)
+              tma_load_2d(b_dst + a * MN_ATOM_BYTES, &tmB, full_bar(stage), n0 + 64 * a, kc * BLOCK_K);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -148,27 +224,31 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, 0u);
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k);
+      int tile, k0, k1;
+      while (it.next(tile, k0, k1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kc = 0; kc < num_k; ++kc) {
+        for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_base = smem_base + stage * STAGE_BYTES;
           const uint32_t b_base = a_base + A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t a_desc = A_MN ? umma_smem_desc(a_base + k * (UMMA_K * 128), A_TILE_BYTES / 2, 1024)
+            // K-major: step 16 elements (32 B) inside the 128 B swizzle row; MN-major: step 16 k-rows (2 KB)
+            const uint64_t a_desc = A_MN ? umma_smem_desc(a_base + k * (UMMA_K * 128), MN_ATOM_BYTES, 1024)
                                          : umma_smem_desc(a_base + k * (UMMA_K * 2), 0, 1024);
-            const uint64_t b_desc = umma_smem_desc(b_base + k * (UMMA_K * 2), 0, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kc | k) != 0 ? 1u : 0u);
+            const uint64_t b_desc = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), MN_ATOM_BYTES, 1024)
+                                         : umma_smem_desc(b_base + k * (UMMA_K * 2), 0, 1024);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kc > k0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
-          if (kc == num_k - 1) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+          if (kc == k1 - 1) umma_commit(tfull_bar(acc));   // accumulator ready for the epilogue
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -199,92 +279,124 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k);
+    int tile, k0, k1;
+    while (it.next(tile, k0, k1)) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
       const int grow = m0 + row_in_tile;
       const bool row_ok = grow < p.M;
 
+      // stream-K bookkeeping for this segment (GRAD only)
+      const bool sk_partial = stream_k && k0 > 0;                    // tail/middle of a tile: publish, no output
+      const bool sk_finish = stream_k && k0 == 0 && k1 < num_k;      // head of a split tile: add the others' partials
+      int sk_last = blockIdx.x;                                      // last CTA contributing to this tile
+      if (sk_finish) {
+        const long long total = (long long)num_tiles * num_k;
+        const long long tile_end = (long long)(tile + 1) * num_k;
+        while (sk_last + 1 < (int)gridDim.x && total * (sk_last + 1) / gridDim.x < tile_end) ++sk_last;
+        if (lane == 0) {
+          for (int c = blockIdx.x + 1; c <= sk_last; ++c) {
+            const int* flag = p.sk_flags + c * NUM_EPI_WARPS + ew;
+            uint32_t spins = 0;
+            uint64_t t_start = 0;
+            while (ld_acquire_gpu(flag) == 0) {
+              if ((++spins & 0x3FFu) == 0) {
+                const uint64_t now = global_timer_ns();
+                if (t_start == 0) t_start = now;
+                else if (now - t_start > 20000000000ull) __trap();
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BLOCK_N + half * (BLOCK_N / 2) + ((uint32_t)(32 * q) << 16);
 
-      uint32_t r[2][32];
-      tmem_ld_32x32(t_base, r[0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < 4) tmem_ld_32x32(t_base + 32 * (c + 1), r[(c + 1) & 1]);
-        const uint32_t(&v)[32] = r[c & 1];
-        const int col0 = n0 + half * (BLOCK_N / 2) + 32 * c;
-
+      // One 32-row x 32-column chunk held in registers (thread = row, v[j] = column col0 + j).
+      auto process_chunk = [&](uint32_t(&v)[32], const int c) {
+        const int col_in_tile = half * (BLOCK_N / 2) + 32 * c;
+        const int col0 = n0 + col_in_tile;
         if constexpr (MODE == MODE_FWD) {
-          const int wdiag0 = p.row_offset + m0 + 32 * q;   // positive column of this warp's first row
-          const bool has_diag = (wdiag0 < col0 + 32) && (col0 < wdiag0 + 32);
-          const bool edge = (col0 + 32 > p.N) || (m0 + BLOCK_M > p.M);
+          // ---- scores -> softplus / sigmoid.  Every element first takes the negative-pair path;
+          //      the (rare) chunk holding this warp's positives is corrected afterwards.
+          if ((col0 + 32 > p.N) || (m0 + BLOCK_M > p.M)) {
+            // edge tile: rows/columns beyond the problem read as s = 0 (TMA zero fill); push them to a
+            // large negative score so that softplus, sigmoid and sigma*x all vanish exactly
+            const int nvalid = row_ok ? p.N - col0 : 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= nvalid) v[j] = __float_as_uint(kMaskedScore);
+          }
           uint32_t packed[16];
-          if (!has_diag && !edge) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float sg[2];
+          for (int j = 0; j < 32; j += 2) {
+            float sg[2];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float s = __uint_as_float(v[j + h]);
-                const float x = s * tau;
-                const float e = ex2_approx(-fabsf(s * tau_l2));
-                const float d = 1.f + e;
-                const float rr = rcp_approx(d);
-                const float lp = lg2_approx(d);
-                neg_sum += fmaf(lp, 0.6931471805599453f, fmaxf(x, 0.f));
-                const float sig = x >= 0.f ? rr : 1.f - rr;
-                dtn_sum = fmaf(sig, x, dtn_sum);
-                sg[h] = sig;
-              }
-              packed[j >> 1] = pack_bf16x2(sg[0], sg[1]);
+            for (int h = 0; h < 2; ++h) {
+              float sp;
+              neg_terms(__uint_as_float(v[j + h]), tau, tau_l2, sp, sg[h]);
+              neg_sum += sp;
+              dtn_sum = fmaf(sg[h], __uint_as_float(v[j + h]) * tau, dtn_sum);
             }
-          } else {
-            const int dcol = p.row_offset + grow;
+            packed[j >> 1] = pack_bf16x2(sg[0], sg[1]);
+          }
+          const int dj = p.row_offset + grow - col0;          // this row's positive sits at v[dj] if 0 <= dj < 32
+          if (__any_sync(0xffffffffu, row_ok && (unsigned)dj < 32u)) {
+            float s_d = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float sg[2];
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int col = col0 + j + h;
-                const float s = __uint_as_float(v[j + h]);
-                const float x = s * tau;
-                const float e = ex2_approx(-fabsf(s * tau_l2));
-                const float d = 1.f + e;
-                const float rr = rcp_approx(d);
-                const float sp = fmaf(lg2_approx(d), 0.6931471805599453f, fmaxf(x, 0.f));
-                const float sig = x >= 0.f ? rr : 1.f - rr;
-                const bool ok = row_ok && col < p.N;
-                const bool is_diag = ok && col == dcol;
-                if (is_diag) {
-                  // positive pair: softplus(-x) = softplus(x) - x, dL/dx ~ -sigma(-x) = sigma(x) - 1
-                  const float gneg = x >= 0.f ? -(e * rr) : -rr;   // -(1 - sigma(x)) without cancellation
-                  pos_sum += fmaxf(-x, 0.f) + log1pf(e);           // rare path: full-precision softplus(-x)
-                  dtp_sum = fmaf(gneg, x, dtp_sum);
-                  p.gdiag[grow] = gneg;
-                  sg[h] = 0.f;
-                } else if (ok) {
-                  neg_sum += sp;
-                  dtn_sum = fmaf(sig, x, dtn_sum);
-                  sg[h] = sig;
-                } else {
-                  sg[h] = 0.f;
-                }
-              }
-              packed[j >> 1] = pack_bf16x2(sg[0], sg[1]);
+            for (int j = 0; j < 32; ++j) s_d = (j == dj) ? __uint_as_float(v[j]) : s_d;
+            if (row_ok && (unsigned)dj < 32u) {
+              float sp, sg;
+              neg_terms(s_d, tau, tau_l2, sp, sg);              // take back what the loop above added
+              const float x = s_d * tau;
+              neg_sum -= sp;
+              dtn_sum = fmaf(-sg, x, dtn_sum);
+              const float e = expf(-fabsf(x));                  // full precision on the positive pair
+              const float rr = 1.f / (1.f + e);
+              const float gneg = x >= 0.f ? -(e * rr) : -rr;    // -sigma(-x)
+              pos_sum += fmaxf(-x, 0.f) + log1pf(e);            // softplus(-x)
+              dtp_sum = fmaf(gneg, x, dtp_sum);
+              p.gdiag[grow] = gneg;
             }
           }
           if (p.gmat != nullptr && row_ok && col0 < p.ldg) {
-            uint4* dst = reinterpret_cast<uint4*>(p.gmat + (long long)grow * p.ldg + col0);
+            __nv_bfloat16* grow_ptr = p.gmat + (long long)grow * p.ldg + col0;
+            uint4* dst = reinterpret_cast<uint4*>(grow_ptr);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
               dst[k4] = make_uint4(packed[4 * k4], packed[4 * k4 + 1], packed[4 * k4 + 2], packed[4 * k4 + 3]);
+            // Gmat carries 0 on the positives: same thread, later store to the same address wins
+            if ((unsigned)dj < 32u) grow_ptr[dj] = __float2bfloat16_rn(0.f);
           }
         } else {
+          const long long slot_off = (long long)row_in_tile * BLOCK_N + col_in_tile;
+          if (sk_partial) {
+            // raw fp32 partial accumulator -> this CTA's workspace slot (consumed by the tile's head CTA)
+            float4* dst = reinterpret_cast<float4*>(p.sk_slots + (long long)blockIdx.x * SK_SLOT_FLOATS + slot_off);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+              dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]),
+                                    __uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]));
+            return;
+          }
+          if (sk_finish) {
+            for (int cc = blockIdx.x + 1; cc <= sk_last; ++cc) {
+              const float4* src = reinterpret_cast<const float4*>(p.sk_slots + (long long)cc * SK_SLOT_FLOATS + slot_off);
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 a = __ldcg(src + k4);
+                v[4 * k4] = __float_as_uint(__uint_as_float(v[4 * k4]) + a.x);
+                v[4 * k4 + 1] = __float_as_uint(__uint_as_float(v[4 * k4 + 1]) + a.y);
+                v[4 * k4 + 2] = __float_as_uint(__uint_as_float(v[4 * k4 + 2]) + a.z);
+                v[4 * k4 + 3] = __float_as_uint(__uint_as_float(v[4 * k4 + 3]) + a.w);
+              }
+            }
+          }
           if (row_ok) {
             float* dst = p.out + (long long)grow * p.ldo + col0;
             if (col0 + 32 <= p.N) {
@@ -304,11 +416,40 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+      };
+
+      // 4 chunks per warp and tile, software-pipelined over two register buffers; the loop is kept
+      // rolled (2 chunk bodies in the binary) so that the epilogue stays inside the instruction cache
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(t_base, ra);
+#pragma unroll 1
+      for (int cp = 0; cp < 2; ++cp) {
+        tmem_ld_wait();
+        tmem_ld_32x32(t_base + 32 * (2 * cp + 1), rb);
+        process_chunk(ra, 2 * cp);
+        tmem_ld_wait();
+        if (cp == 0) {
+          tmem_ld_32x32(t_base + 64, ra);
+        } else {
+          // every TMEM read of this accumulator stage has landed: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        process_chunk(rb, 2 * cp + 1);
       }
-      // all TMEM reads of this accumulator stage are complete (wait::ld above)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+
+      if constexpr (MODE == MODE_GRAD) {
+        if (sk_partial) {
+          __threadfence();          // partial tile visible device-wide before the flag
+          __syncwarp();
+          if (lane == 0) st_release_gpu(p.sk_flags + blockIdx.x * NUM_EPI_WARPS + ew, 1);
+        } else if (sk_finish) {
+          __syncwarp();             // all lanes have consumed the partials: re-arm the flags for the next launch
+          if (lane == 0)
+            for (int c = blockIdx.x + 1; c <= sk_last; ++c) p.sk_flags[c * NUM_EPI_WARPS + ew] = 0;
+        }
+      }
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1u;

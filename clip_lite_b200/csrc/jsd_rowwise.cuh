@@ -3,7 +3,6 @@
 //   jsd_index_kernel      the reference's estimator (one indexed negative per row,
 //                         loss.py:94-105,204-254) fused forward + backward
 //   normalize_cast_kernel F.normalize (loss.py:94-95) + cast to bf16 + 1/||x||
-//   transpose_bf16_kernel K-major copy of the normalised operand for the grad GEMMs
 //   normalize_bwd_kernel  diagonal (positive-pair) term + Jacobian of F.normalize
 //   finalize_*_kernel     deterministic fp64 reduction of the per-CTA loss partials
 #pragma once
@@ -290,33 +289,6 @@ normalize_cast_kernel(const T* __restrict__ X, int rows, int D, __nv_bfloat16* _
     }
   });
   if (lane == 0) inv_norm[row] = inv;
-}
-
-// out[c, r] = in[r, c] for bf16 matrices (64 x 64 tiles, block (32, 8)).
-__global__ void __launch_bounds__(256)
-transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int cols, long long ld_in,
-                      __nv_bfloat16* __restrict__ out, long long ld_out) {
-  __shared__ __nv_bfloat16 t[64][66];
-  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int r = ty; r < 64; r += 8) {
-    const int gr = r0 + r;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int gc = c0 + 2 * tx + h;
-      t[r][2 * tx + h] = (gr < rows && gc < cols) ? in[(size_t)gr * ld_in + gc] : __float2bfloat16_rn(0.f);
-    }
-  }
-  __syncthreads();
-  for (int c = ty; c < 64; c += 8) {
-    const int gc = c0 + c;
-    if (gc >= cols) continue;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int gr = r0 + 2 * tx + h;
-      if (gr < rows) out[(size_t)gc * ld_out + gr] = t[2 * tx + h][c];
-    }
-  }
 }
 
 // ------------------------------------------------------------------ normalise backward (dense post-pass)

@@ -88,31 +88,29 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
 
 
 # ------------------------------------------------------------------ dense mode
-def normalize_cast(x: torch.Tensor, transpose: bool = False):
-    """(Xn bf16 [rows, D], XnT bf16 [D, ldt] or None, inv_norm fp32 [rows])."""
+_SK_WORKSPACES = {}
+
+
+def streamk_workspace(device) -> torch.Tensor:
+    """Per (device, stream) scratch of the backward GEMMs (stream-K partial tiles + flags).
+    Allocated zeroed once; the kernels leave the flag area zero after every launch."""
+    key = (str(device), _stream())
+    ws = _SK_WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.load().jsd_streamk_workspace_bytes(), dtype=torch.uint8, device=device)
+        _SK_WORKSPACES[key] = ws
+    return ws
+
+
+def normalize_cast(x: torch.Tensor):
+    """(Xn bf16 [rows, D], inv_norm fp32 [rows])."""
     _req(x, "X", ndim=2)
     rows, d = x.shape
     xn = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device)
     inv = torch.empty(rows, dtype=torch.float32, device=x.device)
-    xt = None
-    ldt = 0
-    if transpose:
-        ldt = round_up(rows, 8)
-        xt = torch.empty(d, ldt, dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.call("jsd_normalize_cast", _ptr(x), _code(x), rows, d, _ptr(xn), _ptr(xt), ldt, _ptr(inv), _stream())
-    return xn, xt, inv
-
-
-def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
-    """[rows, cols] bf16 -> [cols, round_up(rows, 8)] bf16."""
-    _req(x, "X", dtype=torch.bfloat16, ndim=2)
-    rows, cols = x.shape
-    ldo = round_up(rows, 8)
-    out = torch.empty(cols, ldo, dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.call("jsd_transpose_bf16", _ptr(x), rows, cols, cols, _ptr(out), ldo, _stream())
-    return out
+        _lib.call("jsd_normalize_cast", _ptr(x), _code(x), rows, d, _ptr(xn), _ptr(inv), _stream())
+    return xn, inv
 
 
 def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int = 0, want_grad: bool = True):
@@ -139,34 +137,32 @@ def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int
     return out4, gmat, gdiag
 
 
-def dense_bwd_du(gmat: torch.Tensor, vt: torch.Tensor, n: int, t: torch.Tensor,
-                 gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dUacc [M, D] fp32 = gamma tau / (M (N-1)) Gmat . V, with vt = V^T [D, ldvt]."""
+def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, rows_out: int, t, gamma):
     _req(gmat, "Gmat", dtype=torch.bfloat16, ndim=2)
-    _req(vt, "VT", dtype=torch.bfloat16, ndim=2)
-    m, ldg = gmat.shape
-    d, ldvt = vt.shape
+    _req(x, "operand", dtype=torch.bfloat16, ndim=2)
+    if gmat.shape[0] != m or gmat.shape[1] < n:
+        raise ValueError(f"Gmat {tuple(gmat.shape)} does not cover the [{m}, {n}] slab")
+    d = x.shape[1]
     tt = _scalar(t, "temperature")
     gg = None if gamma is None else _scalar(gamma, "gamma")
-    out = torch.empty(m, d, dtype=torch.float32, device=gmat.device)
+    out = torch.empty(rows_out, d, dtype=torch.float32, device=gmat.device)
     with torch.cuda.device(gmat.device):
-        _lib.call("jsd_dense_bwd_du", _ptr(gmat), ldg, _ptr(vt), ldvt, m, n, d, _ptr(tt), _ptr(gg), _ptr(out), _stream())
+        ws = streamk_workspace(gmat.device)
+        _lib.call(name, _ptr(gmat), gmat.shape[1], _ptr(x), m, n, d, _ptr(tt), _ptr(gg), _ptr(ws), _ptr(out),
+                  _stream())
     return out
 
 
-def dense_bwd_dv(gmat: torch.Tensor, ut: torch.Tensor, n: int, t: torch.Tensor,
+def dense_bwd_du(gmat: torch.Tensor, v: torch.Tensor, t: torch.Tensor,
                  gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dVacc [N, D] fp32 = gamma tau / (M (N-1)) Gmat^T . U, with ut = U^T [D, ldut]."""
-    _req(gmat, "Gmat", dtype=torch.bfloat16, ndim=2)
-    _req(ut, "UT", dtype=torch.bfloat16, ndim=2)
-    m, ldg = gmat.shape
-    d, ldut = ut.shape
-    tt = _scalar(t, "temperature")
-    gg = None if gamma is None else _scalar(gamma, "gamma")
-    out = torch.empty(n, d, dtype=torch.float32, device=gmat.device)
-    with torch.cuda.device(gmat.device):
-        _lib.call("jsd_dense_bwd_dv", _ptr(gmat), ldg, _ptr(ut), ldut, m, n, d, _ptr(tt), _ptr(gg), _ptr(out), _stream())
-    return out
+    """dUacc [M, D] fp32 = gamma tau / (M (N-1)) Gmat . V  (v = V [N, D] bf16, read in place)."""
+    return _dense_bwd("jsd_dense_bwd_du", gmat, v, gmat.shape[0], v.shape[0], gmat.shape[0], t, gamma)
+
+
+def dense_bwd_dv(gmat: torch.Tensor, u: torch.Tensor, n: int, t: torch.Tensor,
+                 gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dVacc [N, D] fp32 = gamma tau / (M (N-1)) Gmat^T . U  (u = U [M, D] bf16, read in place)."""
+    return _dense_bwd("jsd_dense_bwd_dv", gmat, u, u.shape[0], n, n, t, gamma)
 
 
 def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, partner: torch.Tensor,
@@ -191,19 +187,19 @@ def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, pa
     return dx
 
 
-def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False) -> torch.Tensor:
-    """C [M, N] fp32 = A . B^T on the tcgen05 kernel.  a is [M, K] (K-major) or,
-    with a_mn_major, A^T stored [K, M]; b is [N, K]."""
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major: bool = False,
+              stream_k: bool = True) -> torch.Tensor:
+    """C [M, N] fp32 = A . B^T on the tcgen05 kernel.  a is [M, K] (K-major) or, with a_mn_major,
+    A^T stored [K, M]; b is [N, K] or, with b_mn_major, B^T stored [K, N]."""
     _req(a, "A", dtype=torch.bfloat16, ndim=2)
     _req(b, "B", dtype=torch.bfloat16, ndim=2)
-    if a_mn_major:
-        k, m = a.shape
-    else:
-        m, k = a.shape
-    n, k2 = b.shape
+    k, m = (a.shape if a_mn_major else a.shape[::-1])
+    k2, n = (b.shape if b_mn_major else b.shape[::-1])
     if k != k2:
         raise ValueError("gemm_bf16: K mismatch")
     out = torch.empty(m, n, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        _lib.call("jsd_gemm_bf16", _ptr(a), a.shape[1], int(a_mn_major), _ptr(b), k, m, n, k, _ptr(out), _stream())
+        ws = streamk_workspace(a.device) if stream_k else None
+        _lib.call("jsd_gemm_bf16", _ptr(a), a.shape[1], int(a_mn_major), _ptr(b), b.shape[1], int(b_mn_major),
+                  m, n, k, _ptr(ws), _ptr(out), _stream())
     return out

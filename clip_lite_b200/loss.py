@@ -109,27 +109,28 @@ class GlobalDiscriminatorDot(nn.Module):
 
 
 def _forward_block_twice(block: MILinearBlock, x: torch.Tensor) -> torch.Tensor:
-    """Run a projection head once while leaving its BatchNorm buffers exactly as
-    the reference's two passes (positives, then the permuted negatives) leave
-    them: both passes see the same batch statistics s, so after the first
-    update r1 = (1-m) r0 + m s the second is r2 = (2-m) r1 - (1-m) r0."""
+    """Run a projection head once while leaving its BatchNorm buffers exactly as the
+    reference's two passes (positives, then the permuted negatives) leave them.  Both
+    passes see the same batch statistics s, so the two updates r <- (1-m) r + m s
+    collapse into one update with momentum m' = 1 - (1-m)^2 = m (2 - m); the buffers
+    are therefore only ever written by BatchNorm itself (never in place behind
+    autograd's back), and ``num_batches_tracked`` advances by two."""
     bn = block.feature_nonlinear[1] if isinstance(block, MILinearBlock) else None
     replay = block.training and isinstance(bn, nn.BatchNorm1d) and bn.track_running_stats \
         and bn.running_mean is not None
     if not replay:
         return block(x)
-    mean0, var0 = bn.running_mean.clone(), bn.running_var.clone()
-    out = block(x)
+    momentum = bn.momentum
+    if momentum is None:
+        # cumulative average: factors 1/(n+1) then 1/(n+2) collapse into 2/(n+2)
+        bn.momentum = 2.0 / (int(bn.num_batches_tracked) + 2.0)
+    else:
+        bn.momentum = momentum * (2.0 - momentum)
+    try:
+        out = block(x)
+    finally:
+        bn.momentum = momentum
     with torch.no_grad():
-        if bn.momentum is None:                       # cumulative average: factor 1/n
-            n1 = bn.num_batches_tracked.to(mean0.dtype)
-            for buf, old in ((bn.running_mean, mean0), (bn.running_var, var0)):
-                stat = old + (buf - old) * n1
-                buf.add_((stat - buf) / (n1 + 1))
-        else:
-            m = bn.momentum
-            bn.running_mean.mul_(2.0 - m).sub_(mean0, alpha=1.0 - m)
-            bn.running_var.mul_(2.0 - m).sub_(var0, alpha=1.0 - m)
         bn.num_batches_tracked.add_(1)
     return out
 

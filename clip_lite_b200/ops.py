@@ -96,11 +96,11 @@ class _JSDDenseFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         with torch.autocast("cuda", enabled=False):
             fc, gc = _common(f, g)
-            u, ut, inv_f = K.normalize_cast(fc, transpose=need_grad)
-            v, vt, inv_g = K.normalize_cast(gc, transpose=need_grad)
+            u, inv_f = K.normalize_cast(fc)
+            v, inv_g = K.normalize_cast(gc)
             out4, gmat, gdiag = K.dense_fwd(u, v, t, row_offset=0, want_grad=need_grad)
         if need_grad:
-            ctx.save_for_backward(fc, gc, t, u, v, ut, vt, inv_f, inv_g, gmat, gdiag, out4)
+            ctx.save_for_backward(fc, gc, t, u, v, inv_f, inv_g, gmat, gdiag, out4)
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         stats = out4.clone()
         ctx.mark_non_differentiable(stats)
@@ -108,12 +108,12 @@ class _JSDDenseFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        fc, gc, t, u, v, ut, vt, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
+        fc, gc, t, u, v, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
         b = fc.shape[0]
         with torch.autocast("cuda", enabled=False):
             gamma = grad_loss.float()
-            du = K.dense_bwd_du(gmat, vt, b, t, gamma)
-            dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+            du = K.dense_bwd_du(gmat, v, t, gamma)
+            dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
             df = K.normalize_bwd(fc, inv_f, du, v, 0, gdiag, t, gamma, b)
             dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, b)
         fd, gd, td = ctx.dtypes

@@ -57,13 +57,12 @@ class _GatheredDenseFn(torch.autograd.Function):
         with torch.autocast(f.device.type, enabled=False):
             dt = torch.promote_types(f.dtype, g.dtype)
             fc, gc = f.to(dt).contiguous(), g.to(dt).contiguous()
-            u, ut, inv_f = K.normalize_cast(fc, transpose=need_grad)
-            v, _, inv_g = K.normalize_cast(gc, transpose=False)
+            u, inv_f = K.normalize_cast(fc)
+            v, inv_g = K.normalize_cast(gc)
             v_all = _all_gather_rows(v, world, group) if world > 1 else v
             out4, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
-            vt_all = K.transpose_bf16(v_all) if need_grad else None
         if need_grad:
-            ctx.save_for_backward(fc, gc, t, u, ut, v_all, vt_all, inv_f, inv_g, gmat, gdiag, out4)
+            ctx.save_for_backward(fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag, out4)
         ctx.group, ctx.rank, ctx.world = group, rank, world
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         stats = out4.clone()
@@ -72,14 +71,14 @@ class _GatheredDenseFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        fc, gc, t, u, ut, v_all, vt_all, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
+        fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
         m, n = fc.shape[0], v_all.shape[0]
         with torch.autocast(fc.device.type, enabled=False):
             gamma = grad_loss.float()
             # text side first so that its reduce-scatter is in flight during the image side
-            dv_partial = K.dense_bwd_dv(gmat, ut, n, t, gamma)                 # [N, D], partial over ranks
+            dv_partial = K.dense_bwd_dv(gmat, u, n, t, gamma)                  # [N, D], partial over ranks
             dv = _reduce_scatter_rows(dv_partial, ctx.world, ctx.group) if ctx.world > 1 else dv_partial
-            du = K.dense_bwd_du(gmat, vt_all, n, t, gamma)                     # [M, D], complete
+            du = K.dense_bwd_du(gmat, v_all, t, gamma)                         # [M, D], complete
             df = K.normalize_bwd(fc, inv_f, du, v_all, ctx.rank * m, gdiag, t, gamma, m)
             dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, m)
         fd, gd, td = ctx.dtypes

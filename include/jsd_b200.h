@@ -67,14 +67,9 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
  * autograd's forward / backward.
  */
 
-/* F.normalize (loss.py:94-95) + cast: Xn = bf16(x / max(||x||, 1e-12)), inv_norm = 1 / max(||x||, 1e-12).
- * XnT (optional, may be NULL) receives the transpose [D, ldt] (ldt >= rows, multiple of 8). */
-int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn_bf16, void* XnT_bf16,
-                       int64_t ldt, float* inv_norm, jsd_stream_t stream);
-
-/* Transposed bf16 copy: out[c, r] = in[r, c] (used for the gathered operand in the multi-GPU path). */
-int jsd_transpose_bf16(const void* in_bf16, int64_t rows, int64_t cols, int64_t ld_in, void* out_bf16,
-                       int64_t ld_out, jsd_stream_t stream);
+/* F.normalize (loss.py:94-95) + cast: Xn = bf16(x / max(||x||, 1e-12)), inv_norm = 1 / max(||x||, 1e-12). */
+int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn_bf16, float* inv_norm,
+                       jsd_stream_t stream);
 
 size_t jsd_dense_workspace_bytes(void);
 
@@ -87,14 +82,23 @@ int jsd_dense_fwd(const void* U_bf16, const void* V_bf16, int64_t M, int64_t N, 
                   const float* t_dev, void* Gmat_bf16, int64_t ldg, float* gdiag, void* workspace, float* out4,
                   jsd_stream_t stream);
 
-/* Backward contractions (tensor cores), off-diagonal part, fp32 out:
- *   dUacc [M, D] = gamma tau / (M (N-1)) * Gmat   . V     (VT_bf16 = V^T [D, ldvt], ldvt >= N)
- *   dVacc [N, D] = gamma tau / (M (N-1)) * Gmat^T . U     (UT_bf16 = U^T [D, ldut], ldut >= M)
- * gamma_dev: device scalar upstream gradient (NULL => 1). */
-int jsd_dense_bwd_du(const void* Gmat_bf16, int64_t ldg, const void* VT_bf16, int64_t ldvt, int64_t M, int64_t N,
-                     int64_t D, const float* t_dev, const float* gamma_dev, float* dUacc, jsd_stream_t stream);
-int jsd_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* UT_bf16, int64_t ldut, int64_t M, int64_t N,
-                     int64_t D, const float* t_dev, const float* gamma_dev, float* dVacc, jsd_stream_t stream);
+/* Workspace of the backward contractions (stream-K partial tiles + hand-off flags).  The first
+ * jsd_streamk_flag_bytes() bytes must be ZERO when the buffer is first used; every launch leaves
+ * them zero again.  One buffer per concurrently used stream. */
+size_t jsd_streamk_workspace_bytes(void);
+size_t jsd_streamk_flag_bytes(void);
+
+/* Backward contractions (tensor cores), off-diagonal part, fp32 out; operands are read as they
+ * lie in memory (MN-major UMMA descriptors), nothing is transposed:
+ *   dUacc [M, D] = gamma tau / (M (N-1)) * Gmat   . V     (V [N, D] bf16 unit rows)
+ *   dVacc [N, D] = gamma tau / (M (N-1)) * Gmat^T . U     (U [M, D] bf16 unit rows)
+ * gamma_dev: device scalar upstream gradient (NULL => 1).  sk_workspace may be NULL (no stream-K). */
+int jsd_dense_bwd_du(const void* Gmat_bf16, int64_t ldg, const void* V_bf16, int64_t M, int64_t N, int64_t D,
+                     const float* t_dev, const float* gamma_dev, void* sk_workspace, float* dUacc,
+                     jsd_stream_t stream);
+int jsd_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, int64_t M, int64_t N, int64_t D,
+                     const float* t_dev, const float* gamma_dev, void* sk_workspace, float* dVacc,
+                     jsd_stream_t stream);
 
 /* Positive-pair term + Jacobian of F.normalize:
  *   d_row = acc_row + gamma tau / M_rows * gdiag[row] * partner[row + partner_offset]
@@ -104,10 +108,12 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
                       const void* partner_bf16, int64_t partner_offset, const float* gdiag, const float* t_dev,
                       const float* gamma_dev, int64_t M_rows, void* dX, jsd_stream_t stream);
 
-/* Plain C = A . B^T on the same tcgen05 kernel (fp32 out [M, N]); A [M, K] bf16 (a_mn_major = 0)
- * or A^T [K, lda] (a_mn_major = 1), B [N, K] bf16.  Exposed for the unit tests of the tensor-core path. */
-int jsd_gemm_bf16(const void* A_bf16, int64_t lda, int a_mn_major, const void* B_bf16, int64_t ldb, int64_t M,
-                  int64_t N, int64_t K, float* C, jsd_stream_t stream);
+/* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
+ * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or
+ * B^T [K, ldb] (b_mn_major = 1).  sk_workspace as above (NULL => whole tiles only).
+ * Exposed for the unit tests of the tensor-core path. */
+int jsd_gemm_bf16(const void* A_bf16, int64_t lda, int a_mn_major, const void* B_bf16, int64_t ldb, int b_mn_major,
+                  int64_t M, int64_t N, int64_t K, void* sk_workspace, float* C, jsd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,20 +11,9 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def normalize_cast(x, transpose=False):
+def normalize_cast(x):
     u, n = orc.l2_normalize(x.float())
-    xn = u.bfloat16()
-    xt = None
-    if transpose:
-        xt = torch.zeros(x.shape[1], _round_up(x.shape[0], 8), dtype=torch.bfloat16)
-        xt[:, :x.shape[0]] = xn.t()
-    return xn, xt, (1.0 / n.squeeze(-1)).float()
-
-
-def transpose_bf16(x):
-    out = torch.zeros(x.shape[1], _round_up(x.shape[0], 8), dtype=torch.bfloat16)
-    out[:, :x.shape[0]] = x.t()
-    return out
+    return u.bfloat16(), (1.0 / n.squeeze(-1)).float()
 
 
 def dense_fwd(u, v, t, row_offset=0, want_grad=True):
@@ -42,14 +31,14 @@ def _scale(m, n, t, gamma):
     return g * float(torch.as_tensor(float(t)).exp()) / (m * (n - 1))
 
 
-def dense_bwd_du(gmat, vt, n, t, gamma=None):
-    m = gmat.shape[0]
-    return (_scale(m, n, t, gamma) * (gmat[:, :n].double() @ vt[:, :n].double().t())).float()
+def dense_bwd_du(gmat, v, t, gamma=None):
+    m, n = gmat.shape[0], v.shape[0]
+    return (_scale(m, n, t, gamma) * (gmat[:, :n].double() @ v.double())).float()
 
 
-def dense_bwd_dv(gmat, ut, n, t, gamma=None):
+def dense_bwd_dv(gmat, u, n, t, gamma=None):
     m = gmat.shape[0]
-    return (_scale(m, n, t, gamma) * (gmat[:, :n].double().t() @ ut[:, :m].double().t())).float()
+    return (_scale(m, n, t, gamma) * (gmat[:, :n].double().t() @ u.double())).float()
 
 
 def normalize_bwd(x, inv_norm, acc, partner, partner_offset, gdiag, t, gamma, m_rows):

@@ -39,26 +39,18 @@ def dev_t(t=T0):
 @pytest.mark.parametrize("rows,d", [(7, 8), (64, 128), (100, 1000), (33, 2048), (5, 30)])
 def test_normalize_cast(K, dtype, rows, d):
     x = (torch.randn(rows, d, device="cuda") * 3).to(dtype)
-    xn, xt, inv = K.normalize_cast(x, transpose=True)
+    xn, inv = K.normalize_cast(x)
     ref, n = orc.l2_normalize(x.double())
     assert relerr(inv, 1.0 / n.squeeze(-1)) < 1e-5
     assert (xn.double() - ref).abs().max() < 2 ** -8
-    assert torch.equal(xt[:, :rows], xn.t())
 
 
 def test_normalize_zero_row(K):
     x = torch.zeros(4, 16, device="cuda")
     x[1] = 1.0
-    xn, _, inv = K.normalize_cast(x)
+    xn, inv = K.normalize_cast(x)
     assert torch.isfinite(xn.float()).all() and (xn[0] == 0).all()
     assert float(inv[0]) == pytest.approx(1e12, rel=1e-5)       # 1 / eps, as F.normalize
-
-
-@pytest.mark.parametrize("rows,cols", [(64, 64), (100, 72), (8, 1000), (1024, 128)])
-def test_transpose(K, rows, cols):
-    x = torch.randn(rows, cols, device="cuda").bfloat16()
-    y = K.transpose_bf16(x)
-    assert torch.equal(y[:, :rows], x.t())
 
 
 # ------------------------------------------------------------------ index mode (reference semantics)
@@ -133,27 +125,44 @@ def test_index_vs_reference_golden(K, golden_dir):
 
 # ------------------------------------------------------------------ tensor-core GEMM (tcgen05 + TMA)
 GEMM_SHAPES = [(128, 256, 64), (128, 256, 256), (256, 512, 128), (384, 256, 1024), (300, 520, 200),
-               (64, 8, 72), (1000, 1024, 1000)]
+               (64, 8, 72), (1000, 1024, 1000),
+               (8192, 1024, 1024),      # 256 tiles on 148 SMs: stream-K with split tiles
+               (2432, 2048, 520),       # 152 tiles, ragged K
+               (19000, 256, 192)]       # 149 tiles of 3 k-chunks: a tile split over several CTAs
 
 
+def _operand(rows, k, mn_major):
+    """Logical [rows, k] bf16 operand; stored transposed ([k, rows padded to 8]) when mn_major."""
+    x = torch.randn(rows, k, device="cuda").bfloat16()
+    if not mn_major:
+        return x, x
+    rp = (rows + 7) // 8 * 8
+    xt = torch.zeros(k, rp, device="cuda").bfloat16()
+    xt[:, :rows] = x.t()
+    return x, xt
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
-def test_gemm_k_major(K, m, n, k):
-    a = torch.randn(m, k, device="cuda").bfloat16()
-    b = torch.randn(n, k, device="cuda").bfloat16()
-    c = K.gemm_bf16(a, b)
+def test_gemm_all_operand_layouts(K, m, n, k, a_mn, b_mn):
+    a, a_store = _operand(m, k, a_mn)
+    b, b_store = _operand(n, k, b_mn)
     ref = a.double() @ b.double().t()
-    assert relerr(c, ref) < 1e-5
+    for stream_k in (True, False):
+        c = K.gemm_bf16(a_store, b_store, a_mn_major=a_mn, b_mn_major=b_mn, stream_k=stream_k)[:m, :n]
+        assert relerr(c, ref) < 1e-5, f"stream_k={stream_k}"
 
 
-@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
-def test_gemm_a_mn_major(K, m, n, k):
-    mp = (m + 7) // 8 * 8
-    at = torch.zeros(k, mp, device="cuda").bfloat16()
-    at[:, :m] = torch.randn(k, m, device="cuda").bfloat16()
-    b = torch.randn(n, k, device="cuda").bfloat16()
-    c = K.gemm_bf16(at, b, a_mn_major=True)[:m]
-    ref = at[:, :m].double().t() @ b.double().t()
-    assert relerr(c, ref) < 1e-5
+def test_stream_k_is_repeatable_and_leaves_flags_clear(K):
+    a = torch.randn(8192, 1024, device="cuda").bfloat16()
+    b = torch.randn(1024, 1024, device="cuda").bfloat16()
+    c0 = K.gemm_bf16(a, b)
+    for _ in range(3):
+        assert torch.equal(K.gemm_bf16(a, b), c0)
+    from clip_lite_b200 import _lib
+    ws = K.streamk_workspace(a.device)
+    torch.cuda.synchronize()
+    assert int(ws[:_lib.load().jsd_streamk_flag_bytes()].sum()) == 0
 
 
 # ------------------------------------------------------------------ dense mode
@@ -183,16 +192,16 @@ def test_dense_fwd_stage(K, m, n, d, off):
 
 
 @pytest.mark.parametrize("m,n,d,off", [(128, 128, 64, 0), (1024, 1024, 128, 0), (384, 384, 72, 0),
-                                        (128, 512, 256, 256), (200, 1000, 128, 800), (512, 512, 1024, 0)])
+                                        (128, 512, 256, 256), (200, 1000, 128, 800), (512, 512, 1024, 0),
+                                        (4096, 4096, 1024, 0), (1024, 8192, 1024, 3072)])
 def test_dense_bwd_stage(K, m, n, d, off):
     _, v = _unit_bf16(n, d, seed=n + d)
     u = _unit_bf16(n, d, seed=n + d)[0][off:off + m].contiguous()
     t = dev_t()
     gamma = torch.tensor(0.9 * 128.0, device="cuda")
     _, gmat, _ = K.dense_fwd(u, v, t, row_offset=off)
-    ut, vt = K.transpose_bf16(u), K.transpose_bf16(v)
-    du = K.dense_bwd_du(gmat, vt, n, t, gamma)
-    dv = K.dense_bwd_dv(gmat, ut, n, t, gamma)
+    du = K.dense_bwd_du(gmat, v, t, gamma)
+    dv = K.dense_bwd_dv(gmat, u, n, t, gamma)
     # same bf16 Gmat fed to an fp64 contraction
     scale = float(gamma) * np.exp(T0) / (m * (n - 1))
     ref_du = scale * (gmat[:, :n].double() @ v.double())
@@ -212,11 +221,11 @@ def test_dense_pipeline_vs_oracle(K, dtype, b, d):
     f, g = f.to(dtype).cuda(), g.to(dtype).cuda()
     t = dev_t()
     gamma = torch.tensor(0.9, device="cuda")
-    u, ut, inv_f = K.normalize_cast(f, transpose=True)
-    v, vt, inv_g = K.normalize_cast(g, transpose=True)
+    u, inv_f = K.normalize_cast(f)
+    v, inv_g = K.normalize_cast(g)
     out4, gmat, gdiag = K.dense_fwd(u, v, t)
-    du = K.dense_bwd_du(gmat, vt, b, t, gamma)
-    dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+    du = K.dense_bwd_du(gmat, v, t, gamma)
+    dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
     df = K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b)
     dg = K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)
     ref = orc.jsd_dense(f.double(), g.double(), T0)

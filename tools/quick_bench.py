@@ -32,28 +32,28 @@ def main():
         g = (0.6 * f.float() + 0.8 * torch.randn(b, d, device="cuda")).bfloat16()
         t = torch.tensor(2.6593, device="cuda")
         gamma = torch.tensor(0.9, device="cuda")
-        u, ut, inv_f = K.normalize_cast(f, transpose=True)
-        v, vt, inv_g = K.normalize_cast(g, transpose=True)
+        u, inv_f = K.normalize_cast(f)
+        v, inv_g = K.normalize_cast(g)
         out4, gmat, gdiag = K.dense_fwd(u, v, t)
-        du = K.dense_bwd_du(gmat, vt, b, t, gamma)
-        dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+        du = K.dense_bwd_du(gmat, v, t, gamma)
+        dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
         flops = 2.0 * b * b * d
 
         def full():
-            u, ut, inv_f = K.normalize_cast(f, transpose=True)
-            v, vt, inv_g = K.normalize_cast(g, transpose=True)
+            u, inv_f = K.normalize_cast(f)
+            v, inv_g = K.normalize_cast(g)
             out4, gmat, gdiag = K.dense_fwd(u, v, t)
-            du = K.dense_bwd_du(gmat, vt, b, t, gamma)
-            dv = K.dense_bwd_dv(gmat, ut, b, t, gamma)
+            du = K.dense_bwd_du(gmat, v, t, gamma)
+            dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
             K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b)
             K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)
 
         stages = {
-            "normalize_cast+T x2": lambda: (K.normalize_cast(f, True), K.normalize_cast(g, True)),
+            "normalize_cast x2": lambda: (K.normalize_cast(f), K.normalize_cast(g)),
             "dense_fwd": lambda: K.dense_fwd(u, v, t),
             "dense_fwd(loss only)": lambda: K.dense_fwd(u, v, t, want_grad=False),
-            "bwd_du": lambda: K.dense_bwd_du(gmat, vt, b, t, gamma),
-            "bwd_dv": lambda: K.dense_bwd_dv(gmat, ut, b, t, gamma),
+            "bwd_du": lambda: K.dense_bwd_du(gmat, v, t, gamma),
+            "bwd_dv": lambda: K.dense_bwd_dv(gmat, u, b, t, gamma),
             "normalize_bwd x2": lambda: (K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b),
                                          K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)),
             "FULL fwd+bwd": full,

@@ -96,12 +96,14 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
   int grid = (int)(tiles < sms ? tiles : sms);
   // stream-K pays when whole tiles leave part of the last wave idle (e.g. 256 tiles on 148 SMs)
   p.stream_k = 0;
-  if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && tiles > sms && tiles % sms != 0 &&
-      sms <= jsd::SK_MAX_CTAS) {
+  const int n_blocks = (p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N;
+  const int sk_grid = sms / n_blocks * n_blocks;            // whole groups of n_blocks CTAs
+  if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && p.n_fastest && sk_grid >= n_blocks &&
+      tiles > sk_grid && tiles % sk_grid != 0 && sk_grid * 16 >= sms * 15 && sk_grid <= jsd::SK_MAX_CTAS) {
     p.stream_k = 1;
     p.sk_flags = reinterpret_cast<int*>(sk_workspace);
     p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
-    grid = sms;
+    grid = sk_grid;
   }
   if (grid_out) *grid_out = grid;
   kern<<<grid, jsd::GEMM_THREADS, jsd::GEMM_SMEM_BYTES, st>>>(tmA, tmB, p);

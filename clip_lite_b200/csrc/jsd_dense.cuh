@@ -19,10 +19,10 @@
 // (tfull/tempty) so the epilogue of one tile overlaps the MMAs of the next.
 //
 // Scheduling: FWD walks whole 128x256 tiles round-robin.  The GRAD GEMMs (256 tiles of
-// 128 k-chunks on 148 SMs at B=8192, D=1024 -> 1.73 waves) use stream-K: the
-// (tile, k-chunk) space is cut into one contiguous range per CTA; a CTA that ends up
-// with the tail of a tile publishes its fp32 partial accumulator to a workspace slot, the
-// CTA holding the head of that tile adds the partials in its epilogue.
+// 128 k-chunks on 148 SMs at B=8192, D=1024 -> 1.73 waves) use stream-K per group of
+// CTAs (see SegmentIter): a CTA that ends up with the tail of a tile publishes its fp32
+// partial accumulator to a workspace slot, the CTA holding the head of that tile adds the
+// partials in its epilogue.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -95,23 +95,36 @@ __device__ __forceinline__ void neg_terms(float s, float tau, float tau_l2, floa
 }
 
 // Work iterator shared by the three roles: yields (tile, k_begin, k_end) segments.
+//
+// Stream-K is applied per GROUP of num_n_blocks CTAs: the (m-block, k-chunk) space is cut into one
+// contiguous range per group and CTA j of a group owns column block j, so the CTAs of a group walk
+// the same A tiles at the same time (the A operand is shared through L2 exactly as in the
+// whole-tile schedule) and every column block of an m-block is split at the same k.
 struct SegmentIter {
   int num_k, num_tiles, stride, tile;   // round-robin whole tiles
-  long long u, u_end;                   // stream-K unit range of this CTA
+  int n_blocks, n_blk;                  // stream-K: column blocks per m-block, this CTA's column block
+  long long u, u_end;                   // stream-K: (m-block, k-chunk) unit range of this CTA's group
   bool stream_k;
-  __device__ SegmentIter(bool sk, int cta, int grid, int tiles, int nk)
-      : num_k(nk), num_tiles(tiles), stride(grid), tile(cta), u(0), u_end(0), stream_k(sk) {
+  __device__ SegmentIter(bool sk, int cta, int grid, int tiles, int nk, int nb)
+      : num_k(nk), num_tiles(tiles), stride(grid), tile(cta), n_blocks(nb), n_blk(0), u(0), u_end(0), stream_k(sk) {
     if (sk) {
-      const long long total = (long long)tiles * nk;
-      u = total * cta / grid;
-      u_end = total * (cta + 1) / grid;
+      const int groups = grid / nb, group = cta / nb;
+      n_blk = cta - group * nb;
+      const long long total = (long long)(tiles / nb) * nk;
+      u = total * group / groups;
+      u_end = total * (group + 1) / groups;
     }
+  }
+  // first unit of the range of the group `cta` belongs to
+  __device__ static long long group_begin(int cta, int grid, int tiles, int nk, int nb) {
+    return (long long)(tiles / nb) * nk * (cta / nb) / (grid / nb);
   }
   __device__ bool next(int& t, int& k0, int& k1) {
     if (stream_k) {
       if (u >= u_end) return false;
-      t = (int)(u / num_k);
-      k0 = (int)(u - (long long)t * num_k);
+      const int m_blk = (int)(u / num_k);
+      t = m_blk * n_blocks + n_blk;       // n-fastest tile numbering
+      k0 = (int)(u - (long long)m_blk * num_k);
       const long long rem = u_end - u;
       k1 = (k0 + rem < num_k) ? (int)(k0 + rem) : num_k;
       u += k1 - k0;
@@ -188,7 +201,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k);
+      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k, num_n_blocks);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
         int m_blk, n_blk;
@@ -227,7 +240,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k);
+      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k, num_n_blocks);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -279,7 +292,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k);
+    SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k, num_n_blocks);
     int tile, k0, k1;
     while (it.next(tile, k0, k1)) {
       int m_blk, n_blk;
@@ -292,12 +305,14 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool sk_partial = stream_k && k0 > 0;                    // tail/middle of a tile: publish, no output
       const bool sk_finish = stream_k && k0 == 0 && k1 < num_k;      // head of a split tile: add the others' partials
       int sk_last = blockIdx.x;                                      // last CTA contributing to this tile
+      const int sk_step = num_n_blocks;                              // same column block of the next group
       if (sk_finish) {
-        const long long total = (long long)num_tiles * num_k;
-        const long long tile_end = (long long)(tile + 1) * num_k;
-        while (sk_last + 1 < (int)gridDim.x && total * (sk_last + 1) / gridDim.x < tile_end) ++sk_last;
+        const long long m_end = (long long)(tile / num_n_blocks + 1) * num_k;   // end of this m-block's units
+        while (sk_last + sk_step < (int)gridDim.x &&
+               SegmentIter::group_begin(sk_last + sk_step, gridDim.x, num_tiles, num_k, num_n_blocks) < m_end)
+          sk_last += sk_step;
         if (lane == 0) {
-          for (int c = blockIdx.x + 1; c <= sk_last; ++c) {
+          for (int c = blockIdx.x + sk_step; c <= sk_last; c += sk_step) {
             const int* flag = p.sk_flags + c * NUM_EPI_WARPS + ew;
             uint32_t spins = 0;
             uint64_t t_start = 0;
@@ -385,7 +400,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             return;
           }
           if (sk_finish) {
-            for (int cc = blockIdx.x + 1; cc <= sk_last; ++cc) {
+            for (int cc = blockIdx.x + sk_step; cc <= sk_last; cc += sk_step) {
               const float4* src = reinterpret_cast<const float4*>(p.sk_slots + (long long)cc * SK_SLOT_FLOATS + slot_off);
 #pragma unroll
               for (int k4 = 0; k4 < 8; ++k4) {
@@ -447,7 +462,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else if (sk_finish) {
           __syncwarp();             // all lanes have consumed the partials: re-arm the flags for the next launch
           if (lane == 0)
-            for (int c = blockIdx.x + 1; c <= sk_last; ++c) p.sk_flags[c * NUM_EPI_WARPS + ew] = 0;
+            for (int c = blockIdx.x + sk_step; c <= sk_last; c += sk_step) p.sk_flags[c * NUM_EPI_WARPS + ew] = 0;
         }
       }
       if (++acc == ACC_STAGES) {

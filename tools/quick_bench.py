@@ -73,5 +73,28 @@ def main():
         print(f"  {'torch.matmul U@V.T bf16':24s} median {med*1e3:9.1f} us   min {mn*1e3:9.1f} us  {flops/(med*1e-3)/1e12:8.1f} TFLOP/s")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "gemm"):
     main()
+
+
+def gemm_variants():
+    """A/B-layout and stream-K variants of the backward-GEMM shape (development aid)."""
+    m, n, k = 8192, 1024, 8192
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    at = a.t().contiguous()
+    b = torch.randn(n, k, device="cuda").bfloat16()
+    bt = b.t().contiguous()
+    flops = 2.0 * m * n * k
+    print(f"== GEMM variants M={m} N={n} K={k}")
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            for sk in (False, True):
+                fn = lambda: K.gemm_bf16(at if a_mn else a, bt if b_mn else b, a_mn_major=a_mn, b_mn_major=b_mn, stream_k=sk)
+                med, mn = timeit(fn)
+                print(f"  a_mn={int(a_mn)} b_mn={int(b_mn)} stream_k={int(sk)}  median {med*1e3:8.1f} us  min {mn*1e3:8.1f} us  {flops/(med*1e-3)/1e12:7.1f} TFLOP/s")
+    med, mn = timeit(lambda: torch.matmul(a, bt))
+    print(f"  torch.matmul                     median {med*1e3:8.1f} us  min {mn*1e3:8.1f} us  {flops/(med*1e-3)/1e12:7.1f} TFLOP/s")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "gemm":
+    gemm_variants()

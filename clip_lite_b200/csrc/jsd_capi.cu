@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "jsd_dense.cuh"
@@ -80,44 +81,72 @@ int sm_count_cached() {
   return cached;
 }
 
-template <int MODE, bool A_MN, bool B_MN>
+// CTA-group size of the tensor-core kernels: 2 (CTA pairs, 256x256 tiles) whenever there is more than
+// one 128-row block; JSD_CTA_GROUP=1|2 overrides (development / A-B timing).
+int pick_cta_group(int64_t m_rows) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("JSD_CTA_GROUP");
+    forced = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  }
+  if (forced) return forced;
+  return m_rows > jsd::BLOCK_M ? 2 : 1;
+}
+
+template <int MODE, bool A_MN, bool B_MN, int CG>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams p, void* sk_workspace,
                 cudaStream_t st, int* grid_out = nullptr) {
-  auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN>;
+  auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN, CG>;
+  constexpr int smem = jsd::gemm_smem_bytes(CG);
   static bool configured = false;
   if (!configured) {
-    JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, jsd::GEMM_SMEM_BYTES));
+    JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int sms = sm_count_cached();
-  JSD_REQUIRE(sms > 0, "no CUDA device");
-  const long long tiles = (long long)((p.M + jsd::BLOCK_M - 1) / jsd::BLOCK_M) *
-                          ((p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N);
-  int grid = (int)(tiles < sms ? tiles : sms);
-  // stream-K pays when whole tiles leave part of the last wave idle (e.g. 256 tiles on 148 SMs)
-  p.stream_k = 0;
+  JSD_REQUIRE(sms >= CG, "no CUDA device");
+  const int max_workers = sms / CG;                         // a worker = one CTA or one CTA pair
   const int n_blocks = (p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N;
-  const int sk_grid = sms / n_blocks * n_blocks;            // whole groups of n_blocks CTAs
-  if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && p.n_fastest && sk_grid >= n_blocks &&
-      tiles > sk_grid && tiles % sk_grid != 0 && sk_grid * 16 >= sms * 15 && sk_grid <= jsd::SK_MAX_CTAS) {
+  const long long tiles = (long long)((p.M + jsd::BLOCK_M * CG - 1) / (jsd::BLOCK_M * CG)) * n_blocks;
+  int workers = (int)(tiles < max_workers ? tiles : max_workers);
+  // stream-K (opt-in: the caller passes a workspace) balances a ragged last wave, e.g. 128 pair tiles on 74 pairs
+  p.stream_k = 0;
+  const int sk_workers = max_workers / n_blocks * n_blocks;   // whole groups of n_blocks workers
+  if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && p.n_fastest && sk_workers >= n_blocks &&
+      tiles > sk_workers && tiles % sk_workers != 0 && sk_workers * 16 >= max_workers * 15 &&
+      sk_workers * CG <= jsd::SK_MAX_CTAS) {
     p.stream_k = 1;
     p.sk_flags = reinterpret_cast<int*>(sk_workspace);
     p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
-    grid = sk_grid;
+    workers = sk_workers;
   }
+  const int grid = workers * CG;
   if (grid_out) *grid_out = grid;
-  kern<<<grid, jsd::GEMM_THREADS, jsd::GEMM_SMEM_BYTES, st>>>(tmA, tmB, p);
-  JSD_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(jsd::GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  JSD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   return 0;
 }
 
 template <int MODE>
-int launch_gemm_any(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const jsd::GemmParams& p,
-                    void* sk_workspace, cudaStream_t st) {
-  if (a_mn) return b_mn ? launch_gemm<MODE, true, true>(tmA, tmB, p, sk_workspace, st)
-                        : launch_gemm<MODE, true, false>(tmA, tmB, p, sk_workspace, st);
-  return b_mn ? launch_gemm<MODE, false, true>(tmA, tmB, p, sk_workspace, st)
-              : launch_gemm<MODE, false, false>(tmA, tmB, p, sk_workspace, st);
+int launch_gemm_any(bool a_mn, bool b_mn, int cg, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                    const jsd::GemmParams& p, void* sk_workspace, cudaStream_t st) {
+#define JSD_GEMM_CASE(A, B, C) \
+  if (a_mn == A && b_mn == B && cg == C) return launch_gemm<MODE, A, B, C>(tmA, tmB, p, sk_workspace, st);
+  JSD_GEMM_CASE(false, false, 1) JSD_GEMM_CASE(false, true, 1) JSD_GEMM_CASE(true, false, 1) JSD_GEMM_CASE(true, true, 1)
+  JSD_GEMM_CASE(false, false, 2) JSD_GEMM_CASE(false, true, 2) JSD_GEMM_CASE(true, false, 2) JSD_GEMM_CASE(true, true, 2)
+#undef JSD_GEMM_CASE
+  return fail("unsupported GEMM variant");
 }
 
 bool fits_int(int64_t v) { return v > 0 && v < (int64_t)1 << 30; }
@@ -239,9 +268,10 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
     JSD_REQUIRE(ldg >= N && ldg % 64 == 0, "jsd_dense_fwd: ldg must be a multiple of 64 and >= N");
     JSD_REQUIRE((reinterpret_cast<uintptr_t>(Gmat) & 15) == 0, "jsd_dense_fwd: Gmat must be 16-byte aligned");
   }
+  const int cg = pick_cta_group(M);
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, U, D, M, D, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;
-  if (int rc = make_tmap(&tmB, V, D, N, D, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;
+  if (int rc = make_tmap(&tmB, V, D, N, D, jsd::BLOCK_K, jsd::b_rows_per_cta(cg))) return rc;
   jsd::GemmParams p{};
   p.M = (int)M;
   p.N = (int)N;
@@ -255,7 +285,9 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   p.partials = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = 0;
-  if (int rc = launch_gemm<jsd::MODE_FWD, false, false>(tmA, tmB, p, nullptr, st, &grid)) return rc;
+  if (int rc = cg == 2 ? launch_gemm<jsd::MODE_FWD, false, false, 2>(tmA, tmB, p, nullptr, st, &grid)
+                       : launch_gemm<jsd::MODE_FWD, false, false, 1>(tmA, tmB, p, nullptr, st, &grid))
+    return rc;
   const double inv_pos = 1.0 / (double)M;
   const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
   jsd::finalize_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS,
@@ -297,7 +329,8 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
   p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;
   p.out = out;
   p.ldo = D;
-  return launch_gemm_any<jsd::MODE_GRAD>(dv, true, tmA, tmB, p, sk_workspace, (cudaStream_t)stream);
+  return launch_gemm_any<jsd::MODE_GRAD>(dv, true, pick_cta_group(rows), tmA, tmB, p, sk_workspace,
+                                          (cudaStream_t)stream);
 }
 
 int jsd_dense_bwd_du(const void* Gmat, int64_t ldg, const void* V, int64_t M, int64_t N, int64_t D,
@@ -328,6 +361,7 @@ int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
   JSD_REQUIRE(A && B && C, "jsd_gemm_bf16: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(K), "jsd_gemm_bf16: bad shape");
   JSD_REQUIRE(N % 4 == 0, "jsd_gemm_bf16: N must be a multiple of 4");
+  const int cg = pick_cta_group(M);
   CUtensorMap tmA, tmB;
   if (a_mn_major) {
     if (int rc = make_tmap(&tmA, A, M, K, lda, 64, jsd::BLOCK_K)) return rc;     // A^T stored [K, lda]
@@ -337,7 +371,7 @@ int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
   if (b_mn_major) {
     if (int rc = make_tmap(&tmB, B, N, K, ldb, 64, jsd::BLOCK_K)) return rc;     // B^T stored [K, ldb]
   } else {
-    if (int rc = make_tmap(&tmB, B, K, N, ldb, jsd::BLOCK_K, jsd::BLOCK_N)) return rc;
+    if (int rc = make_tmap(&tmB, B, K, N, ldb, jsd::BLOCK_K, jsd::b_rows_per_cta(cg))) return rc;
   }
   jsd::GemmParams p{};
   p.M = (int)M;
@@ -349,7 +383,7 @@ int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
   p.scale = 1.f;
   p.out = C;
   p.ldo = N;
-  return launch_gemm_any<jsd::MODE_GRAD>(a_mn_major != 0, b_mn_major != 0, tmA, tmB, p, sk_workspace,
+  return launch_gemm_any<jsd::MODE_GRAD>(a_mn_major != 0, b_mn_major != 0, cg, tmA, tmB, p, sk_workspace,
                                           (cudaStream_t)stream);
 }
 

@@ -15,14 +15,19 @@
 //
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
 // allocator, warps 4..11 = epilogue (two column halves x four TMEM lane quarters).
-// Pipelines: 4-stage smem ring (full/empty mbarriers), 2-stage TMEM accumulator ring
+// Pipelines: smem ring (full/empty mbarriers), 2-stage TMEM accumulator ring
 // (tfull/tempty) so the epilogue of one tile overlaps the MMAs of the next.
 //
-// Scheduling: FWD walks whole 128x256 tiles round-robin.  The GRAD GEMMs (256 tiles of
-// 128 k-chunks on 148 SMs at B=8192, D=1024 -> 1.73 waves) use stream-K per group of
-// CTAs (see SegmentIter): a CTA that ends up with the tail of a tile publishes its fp32
-// partial accumulator to a workspace slot, the CTA holding the head of that tile adds the
-// partials in its epilogue.
+// CTA pairs (template CG = 2): the kernel is fed from L2, and 128x256 tiles pull 48 KB per
+// 128x256x64 MACs through it.  With tcgen05 cta_group::2 two CTAs of a cluster share one
+// 256x256 tile: each loads its own 128 rows of A and HALF of B (32 KB per CTA and k-chunk,
+// 6 stages), the leader CTA issues M=256 MMAs that read both CTAs' shared memory and write
+// both CTAs' TMEM, and tcgen05.commit multicasts the barrier arrivals to both.
+//
+// Scheduling: FWD walks whole tiles round-robin.  The GRAD GEMMs (1.73 waves at B=8192,
+// D=1024) use stream-K per group of workers (see SegmentIter): a worker that ends up with
+// the tail of a tile publishes its fp32 partial accumulator to a workspace slot, the worker
+// holding the head of that tile adds the partials in its epilogue.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -30,24 +35,28 @@
 
 namespace jsd {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int BLOCK_M = 128;    // rows per CTA (TMEM lanes)
+constexpr int BLOCK_N = 256;    // accumulator columns per tile
+constexpr int BLOCK_K = 64;     // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr int MN_ATOM_BYTES = 64 * BLOCK_K * 2;       // one 64-wide MN-major atom: 64 k-rows x 128 B
 constexpr int NUM_CTRL_WARPS = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 32 * (NUM_CTRL_WARPS + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* align slack */ + 256 /* barriers */;
 constexpr int PARTIALS_PER_WARP = 4;                  // pos, neg, dt_pos, dt_neg
-constexpr int SK_SLOT_FLOATS = BLOCK_M * BLOCK_N;     // one fp32 partial accumulator tile
+constexpr int SK_SLOT_FLOATS = BLOCK_M * BLOCK_N;     // one fp32 partial accumulator tile (per CTA)
 constexpr int SK_MAX_CTAS = 256;                      // flags / slots reserved in the workspace
+
+// per-CTA shared-memory budget as a function of the CTA-group size (1 = single CTA, 2 = CTA pair)
+__host__ __device__ constexpr int b_rows_per_cta(int cg) { return BLOCK_N / cg; }
+__host__ __device__ constexpr int stage_bytes(int cg) { return A_TILE_BYTES + b_rows_per_cta(cg) * BLOCK_K * 2; }
+__host__ __device__ constexpr int num_stages(int cg) { return cg == 2 ? 6 : 4; }
+__host__ __device__ constexpr int gemm_smem_bytes(int cg) {
+  return num_stages(cg) * stage_bytes(cg) + 1024 /* align slack */ + 256 /* barriers */;
+}
 
 enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1 };
 
@@ -139,24 +148,33 @@ struct SegmentIter {
   }
 };
 
-template <int MODE, bool A_MN, bool B_MN>
+template <int MODE, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int STAGES = num_stages(CG);
+  constexpr int STAGE_BYTES = stage_bytes(CG);
+  constexpr int BN_CTA = b_rows_per_cta(CG);     // rows of the B operand this CTA stages
+  constexpr int TILE_M = BLOCK_M * CG;           // rows of one worker tile
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
-  auto tfull_bar = [&](int a) { return bar_base + 64u + 8u * a; };
-  auto tempty_bar = [&](int a) { return bar_base + 80u + 8u * a; };
-  const uint32_t tmem_slot = bar_base + 96u;
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 160u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // a "worker" is one CTA (CG = 1) or one CTA pair (CG = 2); rank = this CTA's position in the pair
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int worker = blockIdx.x / CG;
+  const int n_workers = gridDim.x / CG;
 
-  const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m_blocks = (p.M + TILE_M - 1) / TILE_M;
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -173,16 +191,21 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS * CG);   // the leader collects both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -197,35 +220,40 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (every CTA stages its own A rows / B rows)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k, num_n_blocks);
+      // completion bytes of both CTAs of a pair are counted on the LEADER's full barrier
+      const uint32_t full0 = (CG == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      auto load = [&](uint32_t dst, const CUtensorMap* m, int s, int c0, int c1) {
+        if constexpr (CG == 2) tma_load_2d_pair(dst, m, full0 + 8u * s, c0, c1);
+        else tma_load_2d(dst, m, full0 + 8u * s, c0, c1);
+      };
+      SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        const int m0 = m_blk * TILE_M + rank * BLOCK_M;     // this CTA's A rows
+        const int n0 = n_blk * BLOCK_N + rank * BN_CTA;     // this CTA's share of the B rows
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES * CG);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_TILE_BYTES;
           if constexpr (!A_MN) {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m0);
+            load(a_dst, &tmA, stage, kc * BLOCK_K, m0);
           } else {
             // A stored [K, M] with M contiguous: 64-wide MN atoms of 64 k-rows each
 #pragma unroll
-            for (int a = 0; a < BLOCK_M / 64; ++a)
-              tma_load_2d(a_dst + a * MN_ATOM_BYTES, &tmA, full_bar(stage), m0 + 64 * a, kc * BLOCK_K);
+            for (int a = 0; a < BLOCK_M / 64; ++a) load(a_dst + a * MN_ATOM_BYTES, &tmA, stage, m0 + 64 * a, kc * BLOCK_K);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(b_dst, &tmB, full_bar(stage), kc * BLOCK_K, n0);
+            load(b_dst, &tmB, stage, kc * BLOCK_K, n0);
           } else {
 #pragma unroll
-            for (int a = 0; a < BLOCK_N / 64; ++a)
-              tma_load_2d(b_dst + a * MN_ATOM_BYTES, &tmB, full_bar(stage), n0 + 64 * a, kc * BLOCK_K);
+            for (int a = 0; a < BN_CTA / 64; ++a) load(b_dst + a * MN_ATOM_BYTES, &tmB, stage, n0 + 64 * a, kc * BLOCK_K);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -235,12 +263,12 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    // ===================================================== MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k, num_n_blocks);
+      SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -258,10 +286,18 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                          : umma_smem_desc(a_base + k * (UMMA_K * 2), 0, 1024);
             const uint64_t b_desc = B_MN ? umma_smem_desc(b_base + k * (UMMA_K * 128), MN_ATOM_BYTES, 1024)
                                          : umma_smem_desc(b_base + k * (UMMA_K * 2), 0, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kc > k0 || k > 0) ? 1u : 0u);
+            const uint32_t accumulate = (kc > k0 || k > 0) ? 1u : 0u;
+            if constexpr (CG == 2) umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+            else umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
           }
-          umma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
-          if (kc == k1 - 1) umma_commit(tfull_bar(acc));   // accumulator ready for the epilogue
+          // smem slot free (in both CTAs) once these MMAs retire; accumulator ready after the last chunk
+          if constexpr (CG == 2) {
+            umma_commit_pair(empty_bar(stage), 0x3);
+            if (kc == k1 - 1) umma_commit_pair(tfull_bar(acc), 0x3);
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kc == k1 - 1) umma_commit(tfull_bar(acc));
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -274,11 +310,14 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= NUM_CTRL_WARPS) {
-    // ===================================================== epilogue
+    // ===================================================== epilogue (each CTA drains its own 128 TMEM lanes)
     const int ew = warp - NUM_CTRL_WARPS;   // 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int half = ew >> 2;               // column half of the tile
     const int row_in_tile = 32 * q + lane;
+    const uint32_t tempty0 = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const int cta = blockIdx.x;             // stream-K slots / flags are per CTA
+    const int sk_step = num_n_blocks * CG;  // CTA holding the same rows / column block in the next group
 
     float tau = 1.f, tau_l2 = 1.f, gscale = 1.f;
     if constexpr (MODE == MODE_FWD) {
@@ -292,27 +331,26 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    SegmentIter it(stream_k, blockIdx.x, gridDim.x, num_tiles, num_k, num_n_blocks);
+    SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
     int tile, k0, k1;
     while (it.next(tile, k0, k1)) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
-      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      const int m0 = m_blk * TILE_M + rank * BLOCK_M, n0 = n_blk * BLOCK_N;   // this CTA's rows, the tile's columns
       const int grow = m0 + row_in_tile;
       const bool row_ok = grow < p.M;
 
       // stream-K bookkeeping for this segment (GRAD only)
       const bool sk_partial = stream_k && k0 > 0;                    // tail/middle of a tile: publish, no output
       const bool sk_finish = stream_k && k0 == 0 && k1 < num_k;      // head of a split tile: add the others' partials
-      int sk_last = blockIdx.x;                                      // last CTA contributing to this tile
-      const int sk_step = num_n_blocks;                              // same column block of the next group
+      int sk_last = cta;                                             // last CTA contributing to this CTA's rows
       if (sk_finish) {
         const long long m_end = (long long)(tile / num_n_blocks + 1) * num_k;   // end of this m-block's units
         while (sk_last + sk_step < (int)gridDim.x &&
-               SegmentIter::group_begin(sk_last + sk_step, gridDim.x, num_tiles, num_k, num_n_blocks) < m_end)
+               SegmentIter::group_begin((sk_last + sk_step) / CG, n_workers, num_tiles, num_k, num_n_blocks) < m_end)
           sk_last += sk_step;
         if (lane == 0) {
-          for (int c = blockIdx.x + sk_step; c <= sk_last; c += sk_step) {
+          for (int c = cta + sk_step; c <= sk_last; c += sk_step) {
             const int* flag = p.sk_flags + c * NUM_EPI_WARPS + ew;
             uint32_t spins = 0;
             uint64_t t_start = 0;
@@ -392,7 +430,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const long long slot_off = (long long)row_in_tile * BLOCK_N + col_in_tile;
           if (sk_partial) {
             // raw fp32 partial accumulator -> this CTA's workspace slot (consumed by the tile's head CTA)
-            float4* dst = reinterpret_cast<float4*>(p.sk_slots + (long long)blockIdx.x * SK_SLOT_FLOATS + slot_off);
+            float4* dst = reinterpret_cast<float4*>(p.sk_slots + (long long)cta * SK_SLOT_FLOATS + slot_off);
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4)
               dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]),
@@ -400,7 +438,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             return;
           }
           if (sk_finish) {
-            for (int cc = blockIdx.x + sk_step; cc <= sk_last; cc += sk_step) {
+            for (int cc = cta + sk_step; cc <= sk_last; cc += sk_step) {
               const float4* src = reinterpret_cast<const float4*>(p.sk_slots + (long long)cc * SK_SLOT_FLOATS + slot_off);
 #pragma unroll
               for (int k4 = 0; k4 < 8; ++k4) {
@@ -449,7 +487,10 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // every TMEM read of this accumulator stage has landed: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);   // the leader's barrier
+            else mbar_arrive(tempty0 + 8u * acc);
+          }
         }
         process_chunk(rb, 2 * cp + 1);
       }
@@ -458,11 +499,11 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (sk_partial) {
           __threadfence();          // partial tile visible device-wide before the flag
           __syncwarp();
-          if (lane == 0) st_release_gpu(p.sk_flags + blockIdx.x * NUM_EPI_WARPS + ew, 1);
+          if (lane == 0) st_release_gpu(p.sk_flags + cta * NUM_EPI_WARPS + ew, 1);
         } else if (sk_finish) {
           __syncwarp();             // all lanes have consumed the partials: re-arm the flags for the next launch
           if (lane == 0)
-            for (int c = blockIdx.x + sk_step; c <= sk_last; c += sk_step) p.sk_flags[c * NUM_EPI_WARPS + ew] = 0;
+            for (int c = cta + sk_step; c <= sk_last; c += sk_step) p.sk_flags[c * NUM_EPI_WARPS + ew] = 0;
         }
       }
       if (++acc == ACC_STAGES) {
@@ -486,10 +527,11 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal / read this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

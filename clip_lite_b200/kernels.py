@@ -137,7 +137,8 @@ def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int
     return out4, gmat, gdiag
 
 
-def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, rows_out: int, t, gamma):
+def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, rows_out: int, t, gamma,
+               stream_k: bool = False):
     _req(gmat, "Gmat", dtype=torch.bfloat16, ndim=2)
     _req(x, "operand", dtype=torch.bfloat16, ndim=2)
     if gmat.shape[0] != m or gmat.shape[1] < n:
@@ -147,22 +148,24 @@ def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, r
     gg = None if gamma is None else _scalar(gamma, "gamma")
     out = torch.empty(rows_out, d, dtype=torch.float32, device=gmat.device)
     with torch.cuda.device(gmat.device):
-        ws = streamk_workspace(gmat.device)
+        # stream-K is opt-in: on B200 the ragged second wave costs less than the partial-tile exchange
+        # (the chip is power-limited, idle SMs let the busy ones clock higher) -- see DESIGN.md
+        ws = streamk_workspace(gmat.device) if stream_k else None
         _lib.call(name, _ptr(gmat), gmat.shape[1], _ptr(x), m, n, d, _ptr(tt), _ptr(gg), _ptr(ws), _ptr(out),
                   _stream())
     return out
 
 
 def dense_bwd_du(gmat: torch.Tensor, v: torch.Tensor, t: torch.Tensor,
-                 gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 gamma: Optional[torch.Tensor] = None, stream_k: bool = False) -> torch.Tensor:
     """dUacc [M, D] fp32 = gamma tau / (M (N-1)) Gmat . V  (v = V [N, D] bf16, read in place)."""
-    return _dense_bwd("jsd_dense_bwd_du", gmat, v, gmat.shape[0], v.shape[0], gmat.shape[0], t, gamma)
+    return _dense_bwd("jsd_dense_bwd_du", gmat, v, gmat.shape[0], v.shape[0], gmat.shape[0], t, gamma, stream_k)
 
 
 def dense_bwd_dv(gmat: torch.Tensor, u: torch.Tensor, n: int, t: torch.Tensor,
-                 gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 gamma: Optional[torch.Tensor] = None, stream_k: bool = False) -> torch.Tensor:
     """dVacc [N, D] fp32 = gamma tau / (M (N-1)) Gmat^T . U  (u = U [M, D] bf16, read in place)."""
-    return _dense_bwd("jsd_dense_bwd_dv", gmat, u, u.shape[0], n, n, t, gamma)
+    return _dense_bwd("jsd_dense_bwd_dv", gmat, u, u.shape[0], n, n, t, gamma, stream_k)
 
 
 def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, partner: torch.Tensor,

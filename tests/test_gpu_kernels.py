@@ -202,6 +202,9 @@ def test_dense_bwd_stage(K, m, n, d, off):
     _, gmat, _ = K.dense_fwd(u, v, t, row_offset=off)
     du = K.dense_bwd_du(gmat, v, t, gamma)
     dv = K.dense_bwd_dv(gmat, u, n, t, gamma)
+    # the opt-in stream-K schedule must give the same result up to fp32 summation order
+    assert relerr(K.dense_bwd_du(gmat, v, t, gamma, stream_k=True), du) < 1e-5
+    assert relerr(K.dense_bwd_dv(gmat, u, n, t, gamma, stream_k=True), dv) < 1e-5
     # same bf16 Gmat fed to an fp64 contraction
     scale = float(gamma) * np.exp(T0) / (m * (n - 1))
     ref_du = scale * (gmat[:, :n].double() @ v.double())

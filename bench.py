@@ -251,26 +251,57 @@ def run_b200(args, wl):
     ms_per_step = total_ms / args.steps
     value = batch / (ms_per_step * 1e-3)
 
-    # ---- end to end through host buffers (pinned): H2D inputs, fwd+bwd, D2H loss + gradients
-    df_host = torch.empty_like(f_host).pin_memory()
-    dg_host = torch.empty_like(g_host).pin_memory()
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    # ---- end to end through host buffers (pinned): every step copies its inputs host -> device and reads
+    # the loss back.  As in a real input pipeline the H2D copy of step i+1 (copy stream, double-buffered
+    # device staging) overlaps the compute of step i; all copies are inside the timed region.
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(f_dev.detach()), torch.empty_like(g_dev.detach())) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        f = f_host.to(dev, non_blocking=True).requires_grad_(True)
-        g = g_host.to(dev, non_blocking=True).requires_grad_(True)
-        loss = loss_fn(f, g)
-        gf, gg, _ = torch.autograd.grad(loss, (f, g, t_dev))
-        df_host.copy_(gf, non_blocking=True)
-        dg_host.copy_(gg, non_blocking=True)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+    def issue_h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the step that last used this slot has finished
+            stage[slot][0].copy_(f_host, non_blocking=True)
+            stage[slot][1].copy_(g_host, non_blocking=True)
+            h2d_done[slot].record(copy_stream)
 
-    for _ in range(3):
-        e2e_step()
-    e2e_steps = max(5, min(args.steps, 50))
-    e2e_ms = timed(e2e_step, e2e_steps, flush_l2=False) / e2e_steps
+    def e2e_run(steps):
+        main = torch.cuda.current_stream()
+        for ev in consumed:
+            ev.record(main)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record(main)
+        issue_h2d(0)
+        for i in range(steps):
+            slot = i & 1
+            if i + 1 < steps:
+                issue_h2d(slot ^ 1)
+            main.wait_event(h2d_done[slot])
+            f = stage[slot][0].requires_grad_(True)
+            g = stage[slot][1].requires_grad_(True)
+            loss = loss_fn(f, g)
+            torch.autograd.grad(loss, (f, g, t_dev))
+            stage[slot][0].requires_grad_(False)
+            stage[slot][1].requires_grad_(False)
+            consumed[slot].record(main)
+            loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        end.record(main)
+        barrier()
+        tt = torch.tensor(start.elapsed_time(end), device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt)
+
+    e2e_run(3)
+    e2e_steps = max(5, min(args.steps, 100))
+    e2e_ms = e2e_run(e2e_steps) / e2e_steps
     e2e = {"value": batch / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": 2 * rows * dim * 2, "d2h_bytes_per_step": 2 * rows * dim * 2 + 4}
+           "h2d_bytes_per_step": 2 * rows * dim * 2, "d2h_bytes_per_step": 4,
+           "note": "inputs from pinned host memory every step (H2D of step i+1 overlaps step i on a copy stream); "
+                   "the loss is read back to the host every step, gradients stay on the device as in training"}
 
     # ---- roofline of the dominant kernel family (the three tcgen05 GEMM launches of a step),
     # timed live with CUDA events around each launch on the launching stream
@@ -285,7 +316,7 @@ def run_b200(args, wl):
             v_all = v
         gamma = torch.ones((), device=dev)
         t_c = t_dev.detach()
-        _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
+        _, _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
         stages = {
             "fwd": lambda: K.dense_fwd(u, v_all, t_c, row_offset=rank * rows),
             "bwd_du": lambda: K.dense_bwd_du(gmat, v_all, t_c, gamma),

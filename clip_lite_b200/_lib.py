@@ -19,11 +19,17 @@ SIGNATURES = {
     "jsd_sm_count": (c_int, []),
     "jsd_index_workspace_bytes": (c_size_t, [c_int64]),
     "jsd_index_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "jsd_dense_workspace_bytes": (c_size_t, []),
     "jsd_dense_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
-                              c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_dense_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "jsd_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_streamk_workspace_bytes": (c_size_t, []),
     "jsd_streamk_flag_bytes": (c_size_t, []),
     "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
@@ -36,7 +42,7 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
@@ -71,4 +77,6 @@ def check(rc: int, what: str) -> None:
 
 
 def call(name: str, *args) -> None:
-    check(getattr(load(), name)(*args), name)
+    rc = getattr(_lib or load(), name)(*args)
+    if rc != 0:
+        check(rc, name)

@@ -214,7 +214,7 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
 
 extern "C" {
 
-int jsd_abi_version(void) { return 2; }
+int jsd_abi_version(void) { return 3; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -224,7 +224,7 @@ size_t jsd_index_workspace_bytes(int64_t B) { return (size_t)(B > 0 ? B : 0) * 4
 
 int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
                       const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
-                      float* out4, void* dF, void* dG, jsd_stream_t stream) {
+                      float* out4, float* loss_out, void* dF, void* dG, jsd_stream_t stream) {
   JSD_REQUIRE(F && G && t_dev && workspace && out4 && dF && dG, "jsd_index_fwd_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(B) && fits_int(D), "jsd_index_fwd_bwd: B=%lld, D=%lld out of range", (long long)B, (long long)D);
   JSD_REQUIRE((neg_index == nullptr) == (inv_ptr == nullptr) && (inv_ptr == nullptr) == (inv_idx == nullptr),
@@ -237,7 +237,8 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
                                                dG, st)));
   }();
   if (rc) return rc;
-  jsd::finalize_kernel<<<1, 256, 0, st>>>(partials, (int)B, 3, 1.0 / (double)B, 1.0 / (double)B, 1.0, 0.0, out4);
+  jsd::finalize_kernel<<<1, 256, 0, st>>>(partials, (int)B, 3, 1.0 / (double)B, 1.0 / (double)B, 1.0, 0.0, out4,
+                                          loss_out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -257,7 +258,7 @@ size_t jsd_dense_workspace_bytes(void) {
 
 int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                   const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
-                  jsd_stream_t stream) {
+                  float* loss_out, jsd_stream_t stream) {
   JSD_REQUIRE(U && V && t_dev && gdiag && workspace && out4, "jsd_dense_fwd: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_fwd: M=%lld N=%lld D=%lld out of range",
               (long long)M, (long long)N, (long long)D);
@@ -291,7 +292,7 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   const double inv_pos = 1.0 / (double)M;
   const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
   jsd::finalize_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS,
-                                          jsd::PARTIALS_PER_WARP, inv_pos, inv_neg, inv_pos, inv_neg, out4);
+                                          jsd::PARTIALS_PER_WARP, inv_pos, inv_neg, inv_pos, inv_neg, out4, loss_out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -354,6 +355,28 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
   const float inv_rows = (float)(1.0 / (double)M_rows);
   JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(X, rows, D, inv_norm, acc, partner, partner_offset, gdiag, t_dev,
                                                      gamma_dev, inv_rows, dX, st)));
+}
+
+int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U,
+                      void* V, float* inv_f, float* inv_g, void* Gmat, int64_t ldg, float* gdiag, void* workspace,
+                      float* out4, float* loss_out, jsd_stream_t stream) {
+  if (int rc = jsd_normalize_cast(F, dtype, B, D, U, inv_f, stream)) return rc;
+  if (int rc = jsd_normalize_cast(G, dtype, B, D, V, inv_g, stream)) return rc;
+  return jsd_dense_fwd(U, V, B, B, D, 0, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, stream);
+}
+
+int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U, const void* V,
+                       const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg, const float* gdiag,
+                       const float* t_dev, const float* gamma_dev, const float* out4, float* acc_u, float* acc_v,
+                       void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
+  JSD_REQUIRE(out4 && dt_out && acc_u && acc_v, "jsd_dense_backward: null pointer argument");
+  if (int rc = jsd_dense_bwd_du(Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
+  if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
+  if (int rc = jsd_normalize_bwd(F, dtype, B, D, inv_f, acc_u, V, 0, gdiag, t_dev, gamma_dev, B, dF, stream)) return rc;
+  if (int rc = jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, stream)) return rc;
+  jsd::scale_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gamma_dev, out4 + 3, dt_out);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,

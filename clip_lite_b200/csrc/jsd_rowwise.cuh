@@ -232,10 +232,10 @@ jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D,
   }
 }
 
-// out4 = {pos, neg, pos + neg, dL/dt}; deterministic (fixed order, fp64).
+// out4 = {pos, neg, pos + neg, dL/dt} (+ an optional separate copy of the loss); deterministic (fixed order, fp64).
 __global__ void __launch_bounds__(256)
 finalize_kernel(const float* __restrict__ partials, int n, int width, double inv0, double inv1, double inv2,
-                double inv3, float* __restrict__ out4) {
+                double inv3, float* __restrict__ out4, float* __restrict__ loss_out) {
   __shared__ double sh[4][256];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += 256)
@@ -254,6 +254,7 @@ finalize_kernel(const float* __restrict__ partials, int n, int width, double inv
     out4[1] = (float)neg;
     out4[2] = (float)(pos + neg);
     out4[3] = (float)dt;
+    if (loss_out) *loss_out = (float)(pos + neg);
   }
 }
 
@@ -334,6 +335,12 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
       o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), a[d]) - to_f32(x[d]) * inv * dot) * inv);
     }
   });
+}
+
+// dt_out = gamma * dt_in (upstream gradient applied to dL/dt without a host round trip)
+__global__ void scale_scalar_kernel(const float* __restrict__ gamma_dev, const float* __restrict__ dt_in,
+                                    float* __restrict__ dt_out) {
+  *dt_out = (gamma_dev ? *gamma_dev : 1.f) * *dt_in;
 }
 
 }  // namespace jsd

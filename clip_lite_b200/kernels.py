@@ -44,10 +44,26 @@ def _scalar(t: torch.Tensor, name: str) -> torch.Tensor:
     """Device fp32 scalar (0-dim or 1-element) passed by pointer."""
     if not t.is_cuda:
         raise RuntimeError(f"{name} must live on the GPU")
-    t = t.detach()
-    if t.dtype != torch.float32:
-        t = t.float()
-    return t.reshape(1).contiguous()
+    if t.dtype == torch.float32 and t.numel() == 1:
+        return t                       # data_ptr() is all the kernels need; no torch op on the fast path
+    return t.detach().float().reshape(1).contiguous()
+
+
+class _on_device:
+    """`with _on_device(dev)` only when dev is not already current (the common case costs nothing)."""
+
+    def __init__(self, device):
+        self.ctx = None
+        if device.index is not None and device.index != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def round_up(x: int, m: int) -> int:
@@ -61,8 +77,9 @@ def sm_count() -> int:
 # ------------------------------------------------------------------ index mode
 def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[torch.Tensor] = None,
                   inv_ptr: Optional[torch.Tensor] = None, inv_idx: Optional[torch.Tensor] = None):
-    """Reference-semantics estimator, fused fwd+bwd.  Returns (out4, dF, dG):
-    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), dF/dG for upstream gradient 1."""
+    """Reference-semantics estimator, fused fwd+bwd.  Returns (out4, loss, dF, dG):
+    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), loss = 0-dim copy of out4[2], dF/dG for
+    upstream gradient 1."""
     _req(f, "F", ndim=2)
     _req(g, "G", dtype=f.dtype, ndim=2)
     if f.shape != g.shape:
@@ -79,12 +96,13 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
     lib = _lib.load()
     ws = torch.empty(lib.jsd_index_workspace_bytes(b) // 4, dtype=torch.float32, device=f.device)
     out4 = torch.empty(4, dtype=torch.float32, device=f.device)
+    loss = torch.empty((), dtype=torch.float32, device=f.device)
     df = torch.empty_like(f)
     dg = torch.empty_like(g)
-    with torch.cuda.device(f.device):
+    with _on_device(f.device):
         _lib.call("jsd_index_fwd_bwd", _ptr(f), _ptr(g), _code(f), b, d, _ptr(neg_index), _ptr(inv_ptr),
-                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(df), _ptr(dg), _stream())
-    return out4, df, dg
+                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(loss), _ptr(df), _ptr(dg), _stream())
+    return out4, loss, df, dg
 
 
 # ------------------------------------------------------------------ dense mode
@@ -108,13 +126,13 @@ def normalize_cast(x: torch.Tensor):
     rows, d = x.shape
     xn = torch.empty(rows, d, dtype=torch.bfloat16, device=x.device)
     inv = torch.empty(rows, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _lib.call("jsd_normalize_cast", _ptr(x), _code(x), rows, d, _ptr(xn), _ptr(inv), _stream())
     return xn, inv
 
 
 def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int = 0, want_grad: bool = True):
-    """Row-slab dense forward.  Returns (out4, Gmat or None, gdiag)."""
+    """Row-slab dense forward.  Returns (out4, loss, Gmat or None, gdiag)."""
     _req(u, "U", dtype=torch.bfloat16, ndim=2)
     _req(v, "V", dtype=torch.bfloat16, ndim=2)
     m, d = u.shape
@@ -125,16 +143,62 @@ def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int
     lib = _lib.load()
     ws = torch.empty(lib.jsd_dense_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
     out4 = torch.empty(4, dtype=torch.float32, device=u.device)
+    loss = torch.empty((), dtype=torch.float32, device=u.device)
     gdiag = torch.empty(m, dtype=torch.float32, device=u.device)
     gmat = None
     ldg = 0
     if want_grad:
         ldg = round_up(n, 64)
         gmat = torch.empty(m, ldg, dtype=torch.bfloat16, device=u.device)
-    with torch.cuda.device(u.device):
+    with _on_device(u.device):
         _lib.call("jsd_dense_fwd", _ptr(u), _ptr(v), m, n, d, row_offset, _ptr(tt), _ptr(gmat), ldg, _ptr(gdiag),
-                  _ptr(ws), _ptr(out4), _stream())
-    return out4, gmat, gdiag
+                  _ptr(ws), _ptr(out4), _ptr(loss), _stream())
+    return out4, loss, gmat, gdiag
+
+
+def dense_forward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, want_grad: bool = True):
+    """Whole single-GPU forward in ONE library call (normalise+cast x2, tensor-core forward, loss).
+    f, g: [B, D] contiguous CUDA tensors of the same dtype.  Returns
+    (out4, loss, saved) with saved = (u, v, inv_f, inv_g, gmat, gdiag) for dense_backward."""
+    b, d = f.shape
+    dev = f.device
+    tt = _scalar(t, "temperature")
+    lib = _lib.load()
+    u = torch.empty(b, d, dtype=torch.bfloat16, device=dev)
+    v = torch.empty(b, d, dtype=torch.bfloat16, device=dev)
+    # one fp32 allocation for the small vectors: inv_f | inv_g | gdiag | out4 | loss | partials workspace
+    nws = lib.jsd_dense_workspace_bytes() // 4
+    small = torch.empty(3 * b + 8 + nws, dtype=torch.float32, device=dev)
+    inv_f, inv_g, gdiag = small[:b], small[b:2 * b], small[2 * b:3 * b]
+    out4, loss, ws = small[3 * b:3 * b + 4], small[3 * b + 4], small[3 * b + 8:]
+    gmat, ldg = None, 0
+    if want_grad:
+        ldg = round_up(b, 64)
+        gmat = torch.empty(b, ldg, dtype=torch.bfloat16, device=dev)
+    with _on_device(dev):
+        _lib.call("jsd_dense_forward", f.data_ptr(), g.data_ptr(), _code(f), b, d, tt.data_ptr(), u.data_ptr(),
+                  v.data_ptr(), inv_f.data_ptr(), inv_g.data_ptr(), _ptr(gmat), ldg, gdiag.data_ptr(),
+                  ws.data_ptr(), out4.data_ptr(), loss.data_ptr(), _stream())
+    return out4, loss, (u, v, inv_f, inv_g, gmat, gdiag)
+
+
+def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor, out4: torch.Tensor, saved):
+    """Whole single-GPU backward in ONE library call.  Returns (dF, dG, dt)."""
+    u, v, inv_f, inv_g, gmat, gdiag = saved
+    b, d = f.shape
+    dev = f.device
+    tt = _scalar(t, "temperature")
+    gg = _scalar(gamma, "gamma")
+    acc = torch.empty(2, b, d, dtype=torch.float32, device=dev)
+    df = torch.empty_like(f)
+    dg = torch.empty_like(g)
+    dt = torch.empty((), dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        _lib.call("jsd_dense_backward", f.data_ptr(), g.data_ptr(), _code(f), b, d, u.data_ptr(), v.data_ptr(),
+                  inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
+                  tt.data_ptr(), gg.data_ptr(), out4.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(),
+                  df.data_ptr(), dg.data_ptr(), dt.data_ptr(), _stream())
+    return df, dg, dt
 
 
 def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, rows_out: int, t, gamma,
@@ -147,7 +211,7 @@ def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, r
     tt = _scalar(t, "temperature")
     gg = None if gamma is None else _scalar(gamma, "gamma")
     out = torch.empty(rows_out, d, dtype=torch.float32, device=gmat.device)
-    with torch.cuda.device(gmat.device):
+    with _on_device(gmat.device):
         # stream-K is opt-in: on B200 the ragged second wave costs less than the partial-tile exchange
         # (the chip is power-limited, idle SMs let the busy ones clock higher) -- see DESIGN.md
         ws = streamk_workspace(gmat.device) if stream_k else None
@@ -184,7 +248,7 @@ def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, pa
     tt = _scalar(t, "temperature")
     gg = None if gamma is None else _scalar(gamma, "gamma")
     dx = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _lib.call("jsd_normalize_bwd", _ptr(x), _code(x), rows, d, _ptr(inv_norm), _ptr(acc), _ptr(partner),
                   partner_offset, _ptr(gdiag), _ptr(tt), _ptr(gg), m_rows, _ptr(dx), _stream())
     return dx
@@ -201,7 +265,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_m
     if k != k2:
         raise ValueError("gemm_bf16: K mismatch")
     out = torch.empty(m, n, dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with _on_device(a.device):
         ws = streamk_workspace(a.device) if stream_k else None
         _lib.call("jsd_gemm_bf16", _ptr(a), a.shape[1], int(a_mn_major), _ptr(b), b.shape[1], int(b_mn_major),
                   m, n, k, _ptr(ws), _ptr(out), _stream())

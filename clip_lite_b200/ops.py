@@ -75,12 +75,11 @@ class _JSDIndexFn(torch.autograd.Function):
             if neg is not None and neg.n != fc.shape[0]:
                 raise ValueError(f"neg_index has {neg.n} entries for a batch of {fc.shape[0]}")
             ix = neg.on(fc.device) if neg is not None else (None, None, None)
-            out4, df, dg = K.index_fwd_bwd(fc, gc, t, *ix)
+            out4, loss, df, dg = K.index_fwd_bwd(fc, gc, t, *ix)
         ctx.save_for_backward(df, dg, out4)
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
-        stats = out4.clone()
-        ctx.mark_non_differentiable(stats)
-        return out4[2].clone(), stats
+        ctx.mark_non_differentiable(out4)
+        return loss, out4
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
@@ -96,28 +95,20 @@ class _JSDDenseFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         with torch.autocast("cuda", enabled=False):
             fc, gc = _common(f, g)
-            u, inv_f = K.normalize_cast(fc)
-            v, inv_g = K.normalize_cast(gc)
-            out4, gmat, gdiag = K.dense_fwd(u, v, t, row_offset=0, want_grad=need_grad)
+            out4, loss, saved = K.dense_forward(fc, gc, t, want_grad=need_grad)
         if need_grad:
-            ctx.save_for_backward(fc, gc, t, u, v, inv_f, inv_g, gmat, gdiag, out4)
+            ctx.save_for_backward(fc, gc, t, out4, *saved)
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
-        stats = out4.clone()
-        ctx.mark_non_differentiable(stats)
-        return out4[2].clone(), stats
+        ctx.mark_non_differentiable(out4)
+        return loss, out4
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        fc, gc, t, u, v, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
-        b = fc.shape[0]
+        fc, gc, t, out4, *saved = ctx.saved_tensors
         with torch.autocast("cuda", enabled=False):
-            gamma = grad_loss.float()
-            du = K.dense_bwd_du(gmat, v, t, gamma)
-            dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
-            df = K.normalize_bwd(fc, inv_f, du, v, 0, gdiag, t, gamma, b)
-            dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, b)
+            df, dg, dt = K.dense_backward(fc, gc, t, grad_loss, out4, saved)
         fd, gd, td = ctx.dtypes
-        return df.to(fd), dg.to(gd), (gamma * out4[3]).to(td)
+        return df.to(fd), dg.to(gd), dt.to(td)
 
 
 def jsd_index_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[NegativeIndex] = None):

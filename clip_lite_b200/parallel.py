@@ -60,14 +60,13 @@ class _GatheredDenseFn(torch.autograd.Function):
             u, inv_f = K.normalize_cast(fc)
             v, inv_g = K.normalize_cast(gc)
             v_all = _all_gather_rows(v, world, group) if world > 1 else v
-            out4, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
+            out4, loss, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
         if need_grad:
             ctx.save_for_backward(fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag, out4)
         ctx.group, ctx.rank, ctx.world = group, rank, world
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
-        stats = out4.clone()
-        ctx.mark_non_differentiable(stats)
-        return out4[2].clone(), stats
+        ctx.mark_non_differentiable(out4)
+        return loss, out4
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):

@@ -53,12 +53,13 @@ int jsd_sm_count(void);
  * t_dev      device scalar: the `temperature` parameter (tau = exp(t))
  * workspace  >= jsd_index_workspace_bytes(B) bytes
  * out4       device float[4]: {mean softplus(-s_pos), mean softplus(s_neg), their sum, dL/dt}
+ * loss_out   optional (may be NULL) separate device float receiving the loss (out4[2])
  * dF, dG     [B, D] dL/dF, dL/dG for upstream gradient 1 (same dtype as F, G)
  */
 size_t jsd_index_workspace_bytes(int64_t B);
 int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
                       const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
-                      float* out4, void* dF, void* dG, jsd_stream_t stream);
+                      float* out4, float* loss_out, void* dF, void* dG, jsd_stream_t stream);
 
 /* ------------------------------------------------------------------ dense mode
  * All off-diagonal pairs as negatives (BASELINE.json north star); a row slab
@@ -77,10 +78,11 @@ size_t jsd_dense_workspace_bytes(void);
  * U [M, D], V [N, D] bf16 unit rows (D % 8 == 0).  Gmat (optional, NULL => loss only)
  * [M, ldg] bf16 receives sigma(S_ij) with 0 on the positives (ldg % 64 == 0, ldg >= N);
  * gdiag [M] receives -sigma(-S_ii').  out4 = {pos, neg, pos + neg, dL/dt} of
- *   L = mean_i softplus(-S_ii') + (1 / (M (N - 1))) sum_{j != i'} softplus(S_ij). */
+ *   L = mean_i softplus(-S_ii') + (1 / (M (N - 1))) sum_{j != i'} softplus(S_ij);
+ * loss_out (optional, may be NULL) receives a separate copy of L. */
 int jsd_dense_fwd(const void* U_bf16, const void* V_bf16, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                   const float* t_dev, void* Gmat_bf16, int64_t ldg, float* gdiag, void* workspace, float* out4,
-                  jsd_stream_t stream);
+                  float* loss_out, jsd_stream_t stream);
 
 /* Workspace of the backward contractions (stream-K partial tiles + hand-off flags).  The first
  * jsd_streamk_flag_bytes() bytes must be ZERO when the buffer is first used; every launch leaves
@@ -107,6 +109,19 @@ int jsd_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, int
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner_bf16, int64_t partner_offset, const float* gdiag, const float* t_dev,
                       const float* gamma_dev, int64_t M_rows, void* dX, jsd_stream_t stream);
+
+/* Single-GPU convenience (M == N == B, row_offset 0): the whole forward, resp. the whole backward, in
+ * one call, so that the host pays one FFI crossing per autograd direction.
+ *   forward : jsd_normalize_cast(F) , jsd_normalize_cast(G), jsd_dense_fwd
+ *   backward: jsd_dense_bwd_du, jsd_dense_bwd_dv, jsd_normalize_bwd x2, dt_out = gamma * out4[3]
+ * F, G [B, D] in `dtype`; U, V bf16 [B, D]; acc_u, acc_v fp32 [B, D] scratch; dF, dG in `dtype`. */
+int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U_bf16,
+                      void* V_bf16, float* inv_f, float* inv_g, void* Gmat_bf16, int64_t ldg, float* gdiag,
+                      void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
+int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U_bf16,
+                       const void* V_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16, int64_t ldg,
+                       const float* gdiag, const float* t_dev, const float* gamma_dev, const float* out4, float* acc_u,
+                       float* acc_v, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or

@@ -79,7 +79,8 @@ def test_index_vs_oracle(K, dtype, b, d, mode):
     if neg is not None:
         ptr, idx = _csr_inverse(neg, b)
         args = dict(neg_index=neg.int().cuda(), inv_ptr=ptr.cuda(), inv_idx=idx.cuda())
-    out4, df, dg = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), **args)
+    out4, loss, df, dg = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), **args)
+    assert torch.equal(loss, out4[2])
     ref = orc.jsd_index(f.double(), g.double(), T0, neg)
     rdf, rdg, rdt = orc.jsd_index_grads(f.double(), g.double(), T0, neg)
     assert relerr(out4[0], ref["pos"]) < 1e-5
@@ -114,7 +115,7 @@ def test_index_vs_reference_golden(K, golden_dir):
         if neg is not None:
             ptr, idx = _csr_inverse(neg, f.shape[0])
             args = dict(neg_index=neg.int().cuda(), inv_ptr=ptr.cuda(), inv_idx=idx.cuda())
-        out4, df, dg = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(float(z["t"])), **args)
+        out4, _, df, dg = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(float(z["t"])), **args)
         cross = float(z["out_cross_modal_loss"])
         assert abs(float(out4[2]) - cross) <= LOSS_RTOL * abs(cross), path
         # golden grads are d(total_loss) = 0.9 * d(cross)
@@ -179,7 +180,8 @@ def _unit_bf16(b, d, seed, correlated=True):
 def test_dense_fwd_stage(K, m, n, d, off):
     _, v = _unit_bf16(n, d, seed=n + d)
     u = _unit_bf16(n, d, seed=n + d)[0][off:off + m].contiguous()
-    out4, gmat, gdiag = K.dense_fwd(u, v, dev_t(), row_offset=off)
+    out4, loss, gmat, gdiag = K.dense_fwd(u, v, dev_t(), row_offset=off)
+    assert torch.equal(loss, out4[2])
     ref = orc.dense_from_unit(u.double(), v.double(), T0, row_offset=off)
     assert relerr(out4[0], ref["pos"]) < 1e-4
     assert relerr(out4[1], ref["neg"]) < 1e-4
@@ -199,7 +201,7 @@ def test_dense_bwd_stage(K, m, n, d, off):
     u = _unit_bf16(n, d, seed=n + d)[0][off:off + m].contiguous()
     t = dev_t()
     gamma = torch.tensor(0.9 * 128.0, device="cuda")
-    _, gmat, _ = K.dense_fwd(u, v, t, row_offset=off)
+    _, _, gmat, _ = K.dense_fwd(u, v, t, row_offset=off)
     du = K.dense_bwd_du(gmat, v, t, gamma)
     dv = K.dense_bwd_dv(gmat, u, n, t, gamma)
     # the opt-in stream-K schedule must give the same result up to fp32 summation order
@@ -226,7 +228,7 @@ def test_dense_pipeline_vs_oracle(K, dtype, b, d):
     gamma = torch.tensor(0.9, device="cuda")
     u, inv_f = K.normalize_cast(f)
     v, inv_g = K.normalize_cast(g)
-    out4, gmat, gdiag = K.dense_fwd(u, v, t)
+    out4, _, gmat, gdiag = K.dense_fwd(u, v, t)
     du = K.dense_bwd_du(gmat, v, t, gamma)
     dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
     df = K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b)
@@ -241,8 +243,8 @@ def test_dense_pipeline_vs_oracle(K, dtype, b, d):
 
 def test_dense_fwd_loss_only(K):
     u, v = _unit_bf16(256, 128, seed=0)
-    a, gmat, _ = K.dense_fwd(u, v, dev_t(), want_grad=False)
-    b, _, _ = K.dense_fwd(u, v, dev_t(), want_grad=True)
+    a, _, gmat, _ = K.dense_fwd(u, v, dev_t(), want_grad=False)
+    b, _, _, _ = K.dense_fwd(u, v, dev_t(), want_grad=True)
     assert gmat is None and torch.equal(a, b)
 
 
@@ -253,3 +255,25 @@ def test_bad_arguments_fail_loudly(K):
         K.dense_fwd(u, v, dev_t())
     with pytest.raises(RuntimeError):
         K.index_fwd_bwd(torch.randn(4, 8), torch.randn(4, 8), dev_t())   # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_fused_forward_backward_calls_equal_the_staged_calls(K, dtype):
+    """jsd_dense_forward / jsd_dense_backward are exactly the staged entry points in one FFI crossing."""
+    b, d = 512, 256
+    f, g = orc.synth_embeddings(b, d, seed=5, correlated=True)
+    f, g = f.to(dtype).cuda(), g.to(dtype).cuda()
+    t = dev_t()
+    gamma = torch.tensor(0.7, device="cuda")
+    out4, loss, saved = K.dense_forward(f, g, t)
+    df, dg, dt = K.dense_backward(f, g, t, gamma, out4, saved)
+    u, inv_f = K.normalize_cast(f)
+    v, inv_g = K.normalize_cast(g)
+    out4b, lossb, gmat, gdiag = K.dense_fwd(u, v, t)
+    du = K.dense_bwd_du(gmat, v, t, gamma)
+    dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
+    dfb = K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b)
+    dgb = K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)
+    assert torch.equal(out4, out4b) and torch.equal(loss, lossb)
+    assert torch.equal(df, dfb) and torch.equal(dg, dgb)
+    assert float(dt) == pytest.approx(0.7 * float(out4[3]), rel=1e-6)

@@ -34,7 +34,7 @@ def main():
         gamma = torch.tensor(0.9, device="cuda")
         u, inv_f = K.normalize_cast(f)
         v, inv_g = K.normalize_cast(g)
-        out4, gmat, gdiag = K.dense_fwd(u, v, t)
+        out4, _, gmat, gdiag = K.dense_fwd(u, v, t)
         du = K.dense_bwd_du(gmat, v, t, gamma)
         dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
         flops = 2.0 * b * b * d
@@ -42,7 +42,7 @@ def main():
         def full():
             u, inv_f = K.normalize_cast(f)
             v, inv_g = K.normalize_cast(g)
-            out4, gmat, gdiag = K.dense_fwd(u, v, t)
+            out4, _, gmat, gdiag = K.dense_fwd(u, v, t)
             du = K.dense_bwd_du(gmat, v, t, gamma)
             dv = K.dense_bwd_dv(gmat, u, b, t, gamma)
             K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b)

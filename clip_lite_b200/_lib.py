@@ -30,6 +30,7 @@ SIGNATURES = {
     "jsd_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_sum_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "jsd_streamk_workspace_bytes": (c_size_t, []),
     "jsd_streamk_flag_bytes": (c_size_t, []),
     "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
@@ -37,12 +38,12 @@ SIGNATURES = {
     "jsd_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_bwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "jsd_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64,
                               c_void_p, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

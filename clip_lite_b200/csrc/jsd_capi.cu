@@ -97,7 +97,7 @@ template <int MODE, bool A_MN, bool B_MN, int CG>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams p, void* sk_workspace,
                 cudaStream_t st, int* grid_out = nullptr) {
   auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN, CG>;
-  constexpr int smem = jsd::gemm_smem_bytes(CG);
+  constexpr int smem = jsd::gemm_smem_bytes(CG, MODE);
   static bool configured = false;
   if (!configured) {
     JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -185,7 +185,7 @@ int launch_normalize(const void* X, int64_t rows, int64_t D, void* Xn, float* in
 template <typename T>
 int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                          const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
-                         const float* gamma_dev, float inv_rows, void* dX, cudaStream_t st) {
+                         const float* gamma_dev, float inv_rows, void* dX, float* rowdot, cudaStream_t st) {
   const bool vec = (D % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(dX) | reinterpret_cast<uintptr_t>(acc) |
                      reinterpret_cast<uintptr_t>(partner)) & 15) == 0;
@@ -193,11 +193,11 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
   if (vec)
     jsd::normalize_bwd_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
                                                         (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
-                                                        gamma_dev, inv_rows, (T*)dX);
+                                                        gamma_dev, inv_rows, (T*)dX, rowdot);
   else
     jsd::normalize_bwd_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
                                                         (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
-                                                        gamma_dev, inv_rows, (T*)dX);
+                                                        gamma_dev, inv_rows, (T*)dX, rowdot);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -214,7 +214,7 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
 
 extern "C" {
 
-int jsd_abi_version(void) { return 3; }
+int jsd_abi_version(void) { return 4; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -284,6 +284,10 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   p.ldg = ldg;
   p.gdiag = gdiag;
   p.partials = (float*)workspace;
+  if (Gmat) {
+    // epilogue TMA stores: box = 64 columns x 32 rows per warp; rows >= M / columns >= N are clipped
+    if (int rc = make_tmap(&p.tmG, Gmat, N, M, ldg, jsd::COLS_PER_WARP, 32)) return rc;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   int grid = 0;
   if (int rc = cg == 2 ? launch_gemm<jsd::MODE_FWD, false, false, 2>(tmA, tmB, p, nullptr, st, &grid)
@@ -291,8 +295,8 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
     return rc;
   const double inv_pos = 1.0 / (double)M;
   const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
-  jsd::finalize_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS,
-                                          jsd::PARTIALS_PER_WARP, inv_pos, inv_neg, inv_pos, inv_neg, out4, loss_out);
+  jsd::finalize_dense_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS, inv_pos, inv_neg,
+                                                t_dev, out4, loss_out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -348,13 +352,20 @@ int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, int64_t M, in
 
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
-                      const float* gamma_dev, int64_t M_rows, void* dX, jsd_stream_t stream) {
+                      const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, jsd_stream_t stream) {
   JSD_REQUIRE(X && inv_norm && acc && partner && t_dev && dX, "jsd_normalize_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(rows) && fits_int(D) && M_rows > 0, "jsd_normalize_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_rows = (float)(1.0 / (double)M_rows);
   JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(X, rows, D, inv_norm, acc, partner, partner_offset, gdiag, t_dev,
-                                                     gamma_dev, inv_rows, dX, st)));
+                                                     gamma_dev, inv_rows, dX, rowdot, st)));
+}
+
+int jsd_sum_f32(const float* x, int64_t n, float* out, jsd_stream_t stream) {
+  JSD_REQUIRE(x && out && fits_int(n), "jsd_sum_f32: bad argument");
+  jsd::sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, (int)n, out);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U,
@@ -367,16 +378,16 @@ int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_
 
 int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U, const void* V,
                        const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg, const float* gdiag,
-                       const float* t_dev, const float* gamma_dev, const float* out4, float* acc_u, float* acc_v,
+                       const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v, float* rowdot,
                        void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
-  JSD_REQUIRE(out4 && dt_out && acc_u && acc_v, "jsd_dense_backward: null pointer argument");
+  JSD_REQUIRE(dt_out && acc_u && acc_v && rowdot, "jsd_dense_backward: null pointer argument");
   if (int rc = jsd_dense_bwd_du(Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
   if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
-  if (int rc = jsd_normalize_bwd(F, dtype, B, D, inv_f, acc_u, V, 0, gdiag, t_dev, gamma_dev, B, dF, stream)) return rc;
-  if (int rc = jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, stream)) return rc;
-  jsd::scale_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gamma_dev, out4 + 3, dt_out);
-  JSD_CUDA_OK(cudaGetLastError());
-  return 0;
+  if (int rc = jsd_normalize_bwd(F, dtype, B, D, inv_f, acc_u, V, 0, gdiag, t_dev, gamma_dev, B, dF, rowdot, stream))
+    return rc;
+  if (int rc = jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, stream))
+    return rc;
+  return jsd_sum_f32(rowdot, B, dt_out, stream);     // gamma * dL/dt = sum_i <u_i, dU_i>
 }
 
 int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,

@@ -3,7 +3,7 @@
 // One warp-specialised, persistent tcgen05 GEMM kernel, instantiated three ways:
 //
 //   FWD      S = U . V^T                (A = U [M,D] K-major,      B = V [N,D] K-major)
-//            epilogue: x = tau*S -> softplus / sigmoid -> per-CTA loss partials,
+//            epilogue: x = tau*S -> softplus / sigmoid -> per-warp loss partials,
 //            Gmat[i,j] = sigma(x_ij) (bf16, 0 on the positives), gdiag[i] = -sigma(-x_ii')
 //   GRAD_DU  dUacc = scale * Gmat   . V (A = Gmat [M,N] K-major,   B = V [N,D] read MN-major)
 //   GRAD_DV  dVacc = scale * Gmat^T . U (A = Gmat read MN-major,   B = U [M,D] read MN-major)
@@ -13,8 +13,9 @@
 // of a D=1024 problem cannot live in TMEM next to the S tiles).  No operand is ever
 // transposed in memory: the MN-major UMMA descriptors read U, V and Gmat as they lie.
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..11 = epilogue (two column halves x four TMEM lane quarters).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4.. = epilogue
+// (four TMEM lane quarters x 2 or 4 column groups; 16 epilogue warps by default: the softplus/sigmoid
+// epilogue is latency-bound with only two warps per scheduler).
 // Pipelines: smem ring (full/empty mbarriers), 2-stage TMEM accumulator ring
 // (tfull/tempty) so the epilogue of one tile overlaps the MMAs of the next.
 //
@@ -43,24 +44,32 @@ constexpr int ACC_STAGES = 2;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int MN_ATOM_BYTES = 64 * BLOCK_K * 2;       // one 64-wide MN-major atom: 64 k-rows x 128 B
 constexpr int NUM_CTRL_WARPS = 4;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;                             // 4 TMEM lane quarters x 4 column groups
+constexpr int EPI_COL_GROUPS = NUM_EPI_WARPS / 4;
+constexpr int COLS_PER_WARP = 256 / EPI_COL_GROUPS;           // 64 accumulator columns per epilogue warp and tile
+constexpr int CW = COLS_PER_WARP / 4;                         // chunk width 16: 4 register-resident chunks per warp and tile
+constexpr int G_STAGE_BYTES = 32 * COLS_PER_WARP * 2;         // per-warp Gmat staging box: 32 rows x 64 bf16 = 4 KB (128 B rows)
+static_assert(COLS_PER_WARP * 2 == 128, "the Gmat staging box is one 128-byte swizzle row wide");
 constexpr int GEMM_THREADS = 32 * (NUM_CTRL_WARPS + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
-constexpr int PARTIALS_PER_WARP = 4;                  // pos, neg, dt_pos, dt_neg
+constexpr int PARTIALS_PER_WARP = 4;                  // sum sp(-x_pos), sum max(s,0), sum log2(1+e), spare
 constexpr int SK_SLOT_FLOATS = BLOCK_M * BLOCK_N;     // one fp32 partial accumulator tile (per CTA)
 constexpr int SK_MAX_CTAS = 256;                      // flags / slots reserved in the workspace
 
 // per-CTA shared-memory budget as a function of the CTA-group size (1 = single CTA, 2 = CTA pair)
 __host__ __device__ constexpr int b_rows_per_cta(int cg) { return BLOCK_N / cg; }
 __host__ __device__ constexpr int stage_bytes(int cg) { return A_TILE_BYTES + b_rows_per_cta(cg) * BLOCK_K * 2; }
-__host__ __device__ constexpr int num_stages(int cg) { return cg == 2 ? 6 : 4; }
-__host__ __device__ constexpr int gemm_smem_bytes(int cg) {
-  return num_stages(cg) * stage_bytes(cg) + 1024 /* align slack */ + 256 /* barriers */;
+// the forward kernel gives 64 KB to the Gmat staging boxes of its 16 epilogue warps (TMA stores)
+__host__ __device__ constexpr int g_staging_bytes(int mode) { return mode == 0 ? NUM_EPI_WARPS * G_STAGE_BYTES : 0; }
+__host__ __device__ constexpr int num_stages(int cg, int mode) { return mode == 0 ? (cg == 2 ? 5 : 3) : (cg == 2 ? 6 : 4); }
+__host__ __device__ constexpr int gemm_smem_bytes(int cg, int mode) {
+  return num_stages(cg, mode) * stage_bytes(cg) + g_staging_bytes(mode) + 1024 /* align slack */ + 256 /* barriers */;
 }
 
 enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1 };
 
 struct GemmParams {
+  alignas(64) CUtensorMap tmG;   // FWD: Gmat [M, N] bf16 as the target of the epilogue's TMA stores (box 64 x 32)
   int M;            // rows of the output tile space (FWD: image rows; GRAD: rows of the gradient)
   int N;            // cols of the output tile space (FWD: text rows;  GRAD: D)
   int K;            // contraction length
@@ -88,19 +97,16 @@ struct GemmParams {
 // softplus, sigmoid and sigmoid * x are exactly 0 in fp32.
 constexpr float kMaskedScore = -30000.f;
 
-// Negative-pair terms of one score s = <u_i, v_j>:  x = tau s,  sp = softplus(x),  sg = sigmoid(x).
-//   e = exp(-|x|) (MUFU.EX2), r = 1/(1+e) (MUFU.RCP), log1p(e) = e * q(e) with a degree-4 minimax
-//   q on [0, 1] (|error| < 1e-5, FMA pipe) -- two MUFU ops per element instead of three.
-__device__ __forceinline__ void neg_terms(float s, float tau, float tau_l2, float& sp, float& sg) {
-  const float x = s * tau;
+// Negative-pair terms of one raw score s = <u_i, v_j> (x = tau s):
+//   e = exp(-|x|) (MUFU.EX2), d = 1 + e, sigmoid(|x|) = 1/d (MUFU.RCP), sg = sigmoid(x).
+// softplus(x) = max(x, 0) + log(d) is NOT formed per element: the epilogue accumulates sum max(s, 0)
+// (scaled by tau once, in the finalize kernel) and the PRODUCT of the d's of a chunk (each in [1, 2], so
+// 16 of them cannot overflow), and takes one MUFU.LG2 per chunk: log-sum = log-product.
+__device__ __forceinline__ void neg_terms(float s, float tau_l2, float& d, float& sg) {
   const float e = ex2_approx(-fabsf(s * tau_l2));
-  const float rr = rcp_approx(1.f + e);
-  float q = fmaf(e, 0.032151564955711365f, -0.136042982339859f);
-  q = fmaf(e, q, 0.28945469856262207f);
-  q = fmaf(e, q, -0.49190056324005127f);
-  q = fmaf(e, q, 0.9994943737983704f);
-  sp = fmaf(e, q, fmaxf(x, 0.f));
-  sg = x >= 0.f ? rr : 1.f - rr;
+  d = 1.f + e;
+  const float rr = rcp_approx(d);
+  sg = s >= 0.f ? rr : 1.f - rr;
 }
 
 // Work iterator shared by the three roles: yields (tile, k_begin, k_end) segments.
@@ -150,8 +156,9 @@ struct SegmentIter {
 
 template <int MODE, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int STAGES = num_stages(CG);
+jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ GemmParams p) {
+  constexpr int STAGES = num_stages(CG, MODE);
   constexpr int STAGE_BYTES = stage_bytes(CG);
   constexpr int BN_CTA = b_rows_per_cta(CG);     // rows of the B operand this CTA stages
   constexpr int TILE_M = BLOCK_M * CG;           // rows of one worker tile
@@ -159,7 +166,8 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t g_stage_base = smem_base + STAGES * STAGE_BYTES;          // 1024-aligned (FWD only)
+  const uint32_t bar_base = g_stage_base + g_staging_bytes(MODE);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
@@ -313,9 +321,10 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================================================== epilogue (each CTA drains its own 128 TMEM lanes)
     const int ew = warp - NUM_CTRL_WARPS;   // 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int half = ew >> 2;               // column half of the tile
+    const int cgrp = ew >> 2;               // column group of the tile this warp drains
     const int row_in_tile = 32 * q + lane;
     const uint32_t tempty0 = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t g_stage = g_stage_base + ew * G_STAGE_BYTES;   // this warp's Gmat staging box (FWD)
     const int cta = blockIdx.x;             // stream-K slots / flags are per CTA
     const int sk_step = num_n_blocks * CG;  // CTA holding the same rows / column block in the next group
 
@@ -327,7 +336,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const float gamma = p.gamma_dev ? *p.gamma_dev : 1.f;
       gscale = gamma * (p.t_dev ? expf(*p.t_dev) : 1.f) * p.scale;
     }
-    float pos_sum = 0.f, neg_sum = 0.f, dtp_sum = 0.f, dtn_sum = 0.f;
+    float pos_sum = 0.f, relu_sum = 0.f, lg_sum = 0.f;   // sum softplus(-x_pos), sum max(s,0), sum log2(1+e)
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -368,63 +377,70 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + acc * BLOCK_N + half * (BLOCK_N / 2) + ((uint32_t)(32 * q) << 16);
+      const uint32_t t_base = tmem_base + acc * BLOCK_N + cgrp * COLS_PER_WARP + ((uint32_t)(32 * q) << 16);
 
-      // One 32-row x 32-column chunk held in registers (thread = row, v[j] = column col0 + j).
-      auto process_chunk = [&](uint32_t(&v)[32], const int c) {
-        const int col_in_tile = half * (BLOCK_N / 2) + 32 * c;
+      // One 32-row x CW-column chunk held in registers (thread = row, v[j] = column col0 + j).
+      auto process_chunk = [&](uint32_t(&v)[CW], const int c) {
+        const int col_in_tile = cgrp * COLS_PER_WARP + CW * c;
         const int col0 = n0 + col_in_tile;
         if constexpr (MODE == MODE_FWD) {
           // ---- scores -> softplus / sigmoid.  Every element first takes the negative-pair path;
           //      the (rare) chunk holding this warp's positives is corrected afterwards.
-          if ((col0 + 32 > p.N) || (m0 + BLOCK_M > p.M)) {
+          if ((col0 + CW > p.N) || (m0 + BLOCK_M > p.M)) {
             // edge tile: rows/columns beyond the problem read as s = 0 (TMA zero fill); push them to a
             // large negative score so that softplus, sigmoid and sigma*x all vanish exactly
             const int nvalid = row_ok ? p.N - col0 : 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CW; ++j)
               if (j >= nvalid) v[j] = __float_as_uint(kMaskedScore);
           }
-          uint32_t packed[16];
+          uint32_t packed[CW / 2];
+          float dprod = 1.f;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < CW; j += 2) {
             float sg[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              float sp;
-              neg_terms(__uint_as_float(v[j + h]), tau, tau_l2, sp, sg[h]);
-              neg_sum += sp;
-              dtn_sum = fmaf(sg[h], __uint_as_float(v[j + h]) * tau, dtn_sum);
+              const float sv = __uint_as_float(v[j + h]);
+              float d;
+              neg_terms(sv, tau_l2, d, sg[h]);
+              dprod *= d;
+              relu_sum += fmaxf(sv, 0.f);
             }
             packed[j >> 1] = pack_bf16x2(sg[0], sg[1]);
           }
-          const int dj = p.row_offset + grow - col0;          // this row's positive sits at v[dj] if 0 <= dj < 32
-          if (__any_sync(0xffffffffu, row_ok && (unsigned)dj < 32u)) {
+          lg_sum += lg2_approx(dprod);
+          const int dj = p.row_offset + grow - col0;          // this row's positive sits at v[dj] if 0 <= dj < CW
+          if (__any_sync(0xffffffffu, row_ok && (unsigned)dj < (unsigned)CW)) {
             float s_d = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s_d = (j == dj) ? __uint_as_float(v[j]) : s_d;
-            if (row_ok && (unsigned)dj < 32u) {
-              float sp, sg;
-              neg_terms(s_d, tau, tau_l2, sp, sg);              // take back what the loop above added
+            for (int j = 0; j < CW; ++j) s_d = (j == dj) ? __uint_as_float(v[j]) : s_d;
+            if (row_ok && (unsigned)dj < (unsigned)CW) {
+              // take the positive pair back out of the negative sums, then add it in full precision
               const float x = s_d * tau;
-              neg_sum -= sp;
-              dtn_sum = fmaf(-sg, x, dtn_sum);
-              const float e = expf(-fabsf(x));                  // full precision on the positive pair
+              const float e = expf(-fabsf(x));
+              relu_sum -= fmaxf(s_d, 0.f);
+              lg_sum -= log2f(1.f + ex2_approx(-fabsf(s_d * tau_l2)));
               const float rr = 1.f / (1.f + e);
               const float gneg = x >= 0.f ? -(e * rr) : -rr;    // -sigma(-x)
               pos_sum += fmaxf(-x, 0.f) + log1pf(e);            // softplus(-x)
-              dtp_sum = fmaf(gneg, x, dtp_sum);
               p.gdiag[grow] = gneg;
             }
           }
-          if (p.gmat != nullptr && row_ok && col0 < p.ldg) {
-            __nv_bfloat16* grow_ptr = p.gmat + (long long)grow * p.ldg + col0;
-            uint4* dst = reinterpret_cast<uint4*>(grow_ptr);
+          if (p.gmat != nullptr) {
+            // stage the bf16 chunk in this warp's 32 x 64 box (128-byte rows, 128B swizzle: 16-byte piece
+            // index XOR row%8 -> conflict-free v4 stores); one TMA store per warp and tile writes it out
+            const uint32_t row_base = g_stage + lane * 128;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              dst[k4] = make_uint4(packed[4 * k4], packed[4 * k4 + 1], packed[4 * k4 + 2], packed[4 * k4 + 3]);
-            // Gmat carries 0 on the positives: same thread, later store to the same address wins
-            if ((unsigned)dj < 32u) grow_ptr[dj] = __float2bfloat16_rn(0.f);
+            for (int k4 = 0; k4 < CW / 8; ++k4) {
+              const uint32_t piece = (uint32_t)((CW / 8) * c + k4) ^ (uint32_t)(lane & 7);
+              st_shared_v4(row_base + piece * 16, packed[4 * k4], packed[4 * k4 + 1], packed[4 * k4 + 2],
+                           packed[4 * k4 + 3]);
+            }
+            if (row_ok && (unsigned)dj < (unsigned)CW) {     // Gmat carries 0 on the positives
+              const uint32_t piece = (uint32_t)((CW / 8) * c + (dj >> 3)) ^ (uint32_t)(lane & 7);
+              st_shared_u16(row_base + piece * 16 + (dj & 7) * 2, 0);
+            }
           }
         } else {
           const long long slot_off = (long long)row_in_tile * BLOCK_N + col_in_tile;
@@ -432,7 +448,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // raw fp32 partial accumulator -> this CTA's workspace slot (consumed by the tile's head CTA)
             float4* dst = reinterpret_cast<float4*>(p.sk_slots + (long long)cta * SK_SLOT_FLOATS + slot_off);
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4)
+            for (int k4 = 0; k4 < CW / 4; ++k4)
               dst[k4] = make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]),
                                     __uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]));
             return;
@@ -441,7 +457,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int cc = cta + sk_step; cc <= sk_last; cc += sk_step) {
               const float4* src = reinterpret_cast<const float4*>(p.sk_slots + (long long)cc * SK_SLOT_FLOATS + slot_off);
 #pragma unroll
-              for (int k4 = 0; k4 < 8; ++k4) {
+              for (int k4 = 0; k4 < CW / 4; ++k4) {
                 const float4 a = __ldcg(src + k4);
                 v[4 * k4] = __float_as_uint(__uint_as_float(v[4 * k4]) + a.x);
                 v[4 * k4 + 1] = __float_as_uint(__uint_as_float(v[4 * k4 + 1]) + a.y);
@@ -452,9 +468,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (row_ok) {
             float* dst = p.out + (long long)grow * p.ldo + col0;
-            if (col0 + 32 <= p.N) {
+            if (col0 + CW <= p.N) {
 #pragma unroll
-              for (int k4 = 0; k4 < 8; ++k4) {
+              for (int k4 = 0; k4 < CW / 4; ++k4) {
                 float4 o;
                 o.x = __uint_as_float(v[4 * k4]) * gscale;
                 o.y = __uint_as_float(v[4 * k4 + 1]) * gscale;
@@ -464,7 +480,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < CW; ++j)
                 if (col0 + j < p.N) dst[j] = __uint_as_float(v[j]) * gscale;
             }
           }
@@ -473,16 +489,22 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
       // 4 chunks per warp and tile, software-pipelined over two register buffers; the loop is kept
       // rolled (2 chunk bodies in the binary) so that the epilogue stays inside the instruction cache
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32(t_base, ra);
+      if constexpr (MODE == MODE_FWD) {
+        if (p.gmat != nullptr) {       // the previous tile's TMA store must have read the staging box
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+      }
+      uint32_t ra[CW], rb[CW];
+      tmem_ld_chunk<CW>(t_base, ra);
 #pragma unroll 1
       for (int cp = 0; cp < 2; ++cp) {
         tmem_ld_wait();
-        tmem_ld_32x32(t_base + 32 * (2 * cp + 1), rb);
+        tmem_ld_chunk<CW>(t_base + CW * (2 * cp + 1), rb);
         process_chunk(ra, 2 * cp);
         tmem_ld_wait();
         if (cp == 0) {
-          tmem_ld_32x32(t_base + 64, ra);
+          tmem_ld_chunk<CW>(t_base + 2 * CW, ra);
         } else {
           // every TMEM read of this accumulator stage has landed: hand it back to the MMA warp
           tc_fence_before();
@@ -495,6 +517,16 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         process_chunk(rb, 2 * cp + 1);
       }
 
+      if constexpr (MODE == MODE_FWD) {
+        if (p.gmat != nullptr) {
+          fence_proxy_async();         // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmG, g_stage, n0 + cgrp * COLS_PER_WARP, m0 + 32 * q);
+            tma_store_commit();
+          }
+        }
+      }
       if constexpr (MODE == MODE_GRAD) {
         if (sk_partial) {
           __threadfence();          // partial tile visible device-wide before the flag
@@ -512,16 +544,16 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     if constexpr (MODE == MODE_FWD) {
+      if (p.gmat != nullptr && lane == 0) tma_store_wait_all();   // smem must outlive the last store
       pos_sum = warp_sum(pos_sum);
-      neg_sum = warp_sum(neg_sum);
-      dtp_sum = warp_sum(dtp_sum);
-      dtn_sum = warp_sum(dtn_sum);
+      relu_sum = warp_sum(relu_sum);
+      lg_sum = warp_sum(lg_sum);
       if (lane == 0) {
         float* dst = p.partials + ((long long)blockIdx.x * NUM_EPI_WARPS + ew) * PARTIALS_PER_WARP;
         dst[0] = pos_sum;
-        dst[1] = neg_sum;
-        dst[2] = dtp_sum;
-        dst[3] = dtn_sum;
+        dst[1] = relu_sum;
+        dst[2] = lg_sum;
+        dst[3] = 0.f;
       }
     }
   }

@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __restrict__ inv_norm,
                      const float* __restrict__ acc, const __nv_bfloat16* __restrict__ partner,
                      long long partner_offset, const float* __restrict__ gdiag, const float* __restrict__ t_dev,
-                     const float* __restrict__ gamma_dev, float inv_rows, T* __restrict__ dX) {
+                     const float* __restrict__ gamma_dev, float inv_rows, T* __restrict__ dX,
+                     float* __restrict__ rowdot) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -321,6 +322,7 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
     }
   });
   dot = warp_sum(dot) * inv;   // <u, dU>
+  if (rowdot != nullptr && lane == 0) rowdot[row] = dot;   // sum over rows = gamma * dL/dt
   T* o = dX + (size_t)row * D;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
@@ -337,10 +339,48 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
   });
 }
 
-// dt_out = gamma * dt_in (upstream gradient applied to dL/dt without a host round trip)
-__global__ void scale_scalar_kernel(const float* __restrict__ gamma_dev, const float* __restrict__ dt_in,
-                                    float* __restrict__ dt_out) {
-  *dt_out = (gamma_dev ? *gamma_dev : 1.f) * *dt_in;
+// Dense-mode loss: partials rows = {sum softplus(-x_pos), sum max(s, 0), sum log2(1 + e), -} per epilogue warp.
+//   pos = P0 / M,   neg = (tau * P1 + ln2 * P2) / (M (N - 1)),   out4 = {pos, neg, pos + neg, 0}
+// (dL/dt of the dense mode is produced by the backward: it is the sum of the row dots <u_i, dU_i>.)
+__global__ void __launch_bounds__(256)
+finalize_dense_kernel(const float* __restrict__ partials, int n, double inv_pos, double inv_neg,
+                      const float* __restrict__ t_dev, float* __restrict__ out4, float* __restrict__ loss_out) {
+  __shared__ double sh[3][256];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += 256)
+    for (int k = 0; k < 3; ++k) acc[k] += (double)partials[(size_t)i * 4 + k];
+  for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double tau = exp((double)*t_dev);
+    const double pos = sh[0][0] * inv_pos;
+    const double neg = (tau * sh[1][0] + 0.6931471805599453 * sh[2][0]) * inv_neg;
+    out4[0] = (float)pos;
+    out4[1] = (float)neg;
+    out4[2] = (float)(pos + neg);
+    out4[3] = 0.f;
+    if (loss_out) *loss_out = (float)(pos + neg);
+  }
+}
+
+// out = scale_dev * sum(x[0..n)) in a fixed order (fp64): dL/dt = sum_i <u_i, dU_i> of the dense backward
+__global__ void __launch_bounds__(256)
+sum_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)x[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)sh[0];
 }
 
 }  // namespace jsd

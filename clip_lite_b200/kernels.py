@@ -182,7 +182,7 @@ def dense_forward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, want_grad: 
     return out4, loss, (u, v, inv_f, inv_g, gmat, gdiag)
 
 
-def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor, out4: torch.Tensor, saved):
+def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor, saved):
     """Whole single-GPU backward in ONE library call.  Returns (dF, dG, dt)."""
     u, v, inv_f, inv_g, gmat, gdiag = saved
     b, d = f.shape
@@ -192,13 +192,13 @@ def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: tor
     acc = torch.empty(2, b, d, dtype=torch.float32, device=dev)
     df = torch.empty_like(f)
     dg = torch.empty_like(g)
-    dt = torch.empty((), dtype=torch.float32, device=dev)
+    small = torch.empty(b + 1, dtype=torch.float32, device=dev)       # row dots | dt
     with _on_device(dev):
         _lib.call("jsd_dense_backward", f.data_ptr(), g.data_ptr(), _code(f), b, d, u.data_ptr(), v.data_ptr(),
                   inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
-                  tt.data_ptr(), gg.data_ptr(), out4.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(),
-                  df.data_ptr(), dg.data_ptr(), dt.data_ptr(), _stream())
-    return df, dg, dt
+                  tt.data_ptr(), gg.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(), small.data_ptr(),
+                  df.data_ptr(), dg.data_ptr(), small[b:].data_ptr(), _stream())
+    return df, dg, small[b]
 
 
 def _dense_bwd(name: str, gmat: torch.Tensor, x: torch.Tensor, m: int, n: int, rows_out: int, t, gamma,
@@ -234,8 +234,9 @@ def dense_bwd_dv(gmat: torch.Tensor, u: torch.Tensor, n: int, t: torch.Tensor,
 
 def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, partner: torch.Tensor,
                   partner_offset: int, gdiag: Optional[torch.Tensor], t: torch.Tensor,
-                  gamma: Optional[torch.Tensor], m_rows: int) -> torch.Tensor:
-    """Positive-pair term + Jacobian of F.normalize; returns dX in x's dtype."""
+                  gamma: Optional[torch.Tensor], m_rows: int, want_dt: bool = False):
+    """Positive-pair term + Jacobian of F.normalize; returns dX in x's dtype, or (dX, dt) with
+    want_dt: dt = sum_rows <u_row, d_row> = gamma * dL/dt when x are the image rows."""
     _req(x, "X", ndim=2)
     rows, d = x.shape
     _req(inv_norm, "inv_norm", dtype=torch.float32, ndim=1)
@@ -248,10 +249,13 @@ def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, pa
     tt = _scalar(t, "temperature")
     gg = None if gamma is None else _scalar(gamma, "gamma")
     dx = torch.empty_like(x)
+    rowdot = torch.empty(rows + 1, dtype=torch.float32, device=x.device) if want_dt else None
     with _on_device(x.device):
         _lib.call("jsd_normalize_bwd", _ptr(x), _code(x), rows, d, _ptr(inv_norm), _ptr(acc), _ptr(partner),
-                  partner_offset, _ptr(gdiag), _ptr(tt), _ptr(gg), m_rows, _ptr(dx), _stream())
-    return dx
+                  partner_offset, _ptr(gdiag), _ptr(tt), _ptr(gg), m_rows, _ptr(dx), _ptr(rowdot), _stream())
+        if want_dt:
+            _lib.call("jsd_sum_f32", rowdot.data_ptr(), rows, rowdot[rows:].data_ptr(), _stream())
+    return (dx, rowdot[rows]) if want_dt else dx
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major: bool = False,

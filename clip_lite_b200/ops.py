@@ -8,7 +8,8 @@ loss.py:94-105,204-254 and of its backward runs in libjsd_b200.so.
 f, g are the projected features ([B, D]; fp32, bf16 or fp16), t the 0-dim
 `temperature` parameter.  Both return (loss, stats) where loss is the 0-dim
 CROSS_MODAL_LOSS = Em - Ej of loss.py:254 and stats = [pos, neg, loss, dL/dt]
-(detached, for logging without a host sync).
+(detached, for logging without a host sync; the dense mode reports 0 for dL/dt --
+its temperature gradient falls out of the backward pass).
 """
 from __future__ import annotations
 
@@ -97,16 +98,16 @@ class _JSDDenseFn(torch.autograd.Function):
             fc, gc = _common(f, g)
             out4, loss, saved = K.dense_forward(fc, gc, t, want_grad=need_grad)
         if need_grad:
-            ctx.save_for_backward(fc, gc, t, out4, *saved)
+            ctx.save_for_backward(fc, gc, t, *saved)
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         ctx.mark_non_differentiable(out4)
         return loss, out4
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        fc, gc, t, out4, *saved = ctx.saved_tensors
+        fc, gc, t, *saved = ctx.saved_tensors
         with torch.autocast("cuda", enabled=False):
-            df, dg, dt = K.dense_backward(fc, gc, t, grad_loss, out4, saved)
+            df, dg, dt = K.dense_backward(fc, gc, t, grad_loss, saved)
         fd, gd, td = ctx.dtypes
         return df.to(fd), dg.to(gd), dt.to(td)
 

@@ -62,7 +62,7 @@ class _GatheredDenseFn(torch.autograd.Function):
             v_all = _all_gather_rows(v, world, group) if world > 1 else v
             out4, loss, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
         if need_grad:
-            ctx.save_for_backward(fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag, out4)
+            ctx.save_for_backward(fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag)
         ctx.group, ctx.rank, ctx.world = group, rank, world
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         ctx.mark_non_differentiable(out4)
@@ -70,7 +70,7 @@ class _GatheredDenseFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag, out4 = ctx.saved_tensors
+        fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag = ctx.saved_tensors
         m, n = fc.shape[0], v_all.shape[0]
         with torch.autocast(fc.device.type, enabled=False):
             gamma = grad_loss.float()
@@ -78,10 +78,11 @@ class _GatheredDenseFn(torch.autograd.Function):
             dv_partial = K.dense_bwd_dv(gmat, u, n, t, gamma)                  # [N, D], partial over ranks
             dv = _reduce_scatter_rows(dv_partial, ctx.world, ctx.group) if ctx.world > 1 else dv_partial
             du = K.dense_bwd_du(gmat, v_all, t, gamma)                         # [M, D], complete
-            df = K.normalize_bwd(fc, inv_f, du, v_all, ctx.rank * m, gdiag, t, gamma, m)
+            # dL_r/dt falls out of the image side: sum_i <u_i, dU_i> (dU_i is complete on this rank)
+            df, dt = K.normalize_bwd(fc, inv_f, du, v_all, ctx.rank * m, gdiag, t, gamma, m, want_dt=True)
             dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, m)
         fd, gd, td = ctx.dtypes
-        return df.to(fd), dg.to(gd), (gamma * out4[3]).to(td), None
+        return df.to(fd), dg.to(gd), dt.to(td), None
 
 
 def gathered_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group: Optional[object] = None):

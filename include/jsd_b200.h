@@ -77,9 +77,10 @@ size_t jsd_dense_workspace_bytes(void);
 /* Forward: S = tau U V^T on tcgen05 tensor cores, softplus/sigmoid epilogue, S never stored.
  * U [M, D], V [N, D] bf16 unit rows (D % 8 == 0).  Gmat (optional, NULL => loss only)
  * [M, ldg] bf16 receives sigma(S_ij) with 0 on the positives (ldg % 64 == 0, ldg >= N);
- * gdiag [M] receives -sigma(-S_ii').  out4 = {pos, neg, pos + neg, dL/dt} of
+ * gdiag [M] receives -sigma(-S_ii').  out4 = {pos, neg, pos + neg, 0} of
  *   L = mean_i softplus(-S_ii') + (1 / (M (N - 1))) sum_{j != i'} softplus(S_ij);
- * loss_out (optional, may be NULL) receives a separate copy of L. */
+ * loss_out (optional, may be NULL) receives a separate copy of L.  dL/dt of the dense mode comes out of the
+ * backward (jsd_normalize_bwd rowdot): it is the sum over rows of <u_i, dU_i>. */
 int jsd_dense_fwd(const void* U_bf16, const void* V_bf16, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                   const float* t_dev, void* Gmat_bf16, int64_t ldg, float* gdiag, void* workspace, float* out4,
                   float* loss_out, jsd_stream_t stream);
@@ -105,23 +106,27 @@ int jsd_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, int
 /* Positive-pair term + Jacobian of F.normalize:
  *   d_row = acc_row + gamma tau / M_rows * gdiag[row] * partner[row + partner_offset]
  *   dX_row = (d_row - u_row <u_row, d_row>) * inv_norm[row],   u_row = X_row * inv_norm[row]
- * X, dX [rows, D] in `dtype`; acc fp32 [rows, D]; partner bf16 [*, D]; gdiag may be NULL (no positive term). */
+ * X, dX [rows, D] in `dtype`; acc fp32 [rows, D]; partner bf16 [*, D]; gdiag may be NULL (no positive term).
+ * rowdot (optional, may be NULL) [rows] receives <u_row, d_row>; summed over the image rows it is
+ * gamma * dL/dt (jsd_sum_f32 reduces it in a fixed order). */
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner_bf16, int64_t partner_offset, const float* gdiag, const float* t_dev,
-                      const float* gamma_dev, int64_t M_rows, void* dX, jsd_stream_t stream);
+                      const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, jsd_stream_t stream);
+int jsd_sum_f32(const float* x, int64_t n, float* out, jsd_stream_t stream);
 
 /* Single-GPU convenience (M == N == B, row_offset 0): the whole forward, resp. the whole backward, in
  * one call, so that the host pays one FFI crossing per autograd direction.
  *   forward : jsd_normalize_cast(F) , jsd_normalize_cast(G), jsd_dense_fwd
- *   backward: jsd_dense_bwd_du, jsd_dense_bwd_dv, jsd_normalize_bwd x2, dt_out = gamma * out4[3]
- * F, G [B, D] in `dtype`; U, V bf16 [B, D]; acc_u, acc_v fp32 [B, D] scratch; dF, dG in `dtype`. */
+ *   backward: jsd_dense_bwd_du, jsd_dense_bwd_dv, jsd_normalize_bwd x2, dt_out = jsd_sum_f32(rowdot)
+ * F, G [B, D] in `dtype`; U, V bf16 [B, D]; acc_u, acc_v fp32 [B, D] and rowdot fp32 [B] scratch;
+ * dF, dG in `dtype`; dt_out = gamma * dL/dt. */
 int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U_bf16,
                       void* V_bf16, float* inv_f, float* inv_g, void* Gmat_bf16, int64_t ldg, float* gdiag,
                       void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
 int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U_bf16,
                        const void* V_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16, int64_t ldg,
-                       const float* gdiag, const float* t_dev, const float* gamma_dev, const float* out4, float* acc_u,
-                       float* acc_v, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
+                       const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v,
+                       float* rowdot, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or

@@ -18,7 +18,7 @@ def normalize_cast(x):
 
 def dense_fwd(u, v, t, row_offset=0, want_grad=True):
     d = orc.dense_from_unit(u.double(), v.double(), float(t), row_offset)
-    out4 = torch.stack((d["pos"], d["neg"], d["loss"], d["dt"])).float()
+    out4 = torch.stack((d["pos"], d["neg"], d["loss"], torch.zeros_like(d["loss"]))).float()
     gmat = None
     if want_grad:
         gmat = torch.zeros(u.shape[0], _round_up(v.shape[0], 64), dtype=torch.bfloat16)
@@ -41,7 +41,7 @@ def dense_bwd_dv(gmat, u, n, t, gamma=None):
     return (_scale(m, n, t, gamma) * (gmat[:, :n].double().t() @ u.double())).float()
 
 
-def normalize_bwd(x, inv_norm, acc, partner, partner_offset, gdiag, t, gamma, m_rows):
+def normalize_bwd(x, inv_norm, acc, partner, partner_offset, gdiag, t, gamma, m_rows, want_dt=False):
     g = 1.0 if gamma is None else float(gamma)
     rows = x.shape[0]
     d = acc.double()
@@ -50,4 +50,5 @@ def normalize_bwd(x, inv_norm, acc, partner, partner_offset, gdiag, t, gamma, m_
         d = d + c * gdiag.double()[:, None] * partner[partner_offset:partner_offset + rows].double()
     inv = inv_norm.double()[:, None]
     u = x.double() * inv
-    return ((d - u * (u * d).sum(-1, keepdim=True)) * inv).to(x.dtype)
+    dx = ((d - u * (u * d).sum(-1, keepdim=True)) * inv).to(x.dtype)
+    return (dx, (u * d).sum().float()) if want_dt else dx

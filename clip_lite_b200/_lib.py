@@ -31,6 +31,11 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_sum_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "jsd_normalize_cast_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "jsd_dense_backward_image_side": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                              c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_streamk_workspace_bytes": (c_size_t, []),
     "jsd_streamk_flag_bytes": (c_size_t, []),
     "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
@@ -43,7 +48,7 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

@@ -112,9 +112,12 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
   // stream-K (opt-in: the caller passes a workspace) balances a ragged last wave, e.g. 128 pair tiles on 74 pairs
   p.stream_k = 0;
   const int sk_workers = max_workers / n_blocks * n_blocks;   // whole groups of n_blocks workers
+  const long long m_blocks = tiles / n_blocks;
   if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && p.n_fastest && sk_workers >= n_blocks &&
-      tiles > sk_workers && tiles % sk_workers != 0 && sk_workers * 16 >= max_workers * 15 &&
-      sk_workers * CG <= jsd::SK_MAX_CTAS) {
+      m_blocks % (sk_workers / n_blocks) != 0 && tiles > sk_workers && sk_workers * 16 >= max_workers * 15 &&
+      sk_workers * CG <= jsd::SK_MAX_CTAS &&
+      // every group must receive at least one k-chunk of the stream-K m-blocks (no empty ranges)
+      (m_blocks % (sk_workers / n_blocks)) * ((p.K + jsd::BLOCK_K - 1) / jsd::BLOCK_K) >= sk_workers / n_blocks) {
     p.stream_k = 1;
     p.sk_flags = reinterpret_cast<int*>(sk_workspace);
     p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
@@ -157,15 +160,14 @@ int launch_index(const void* F, const void* G, int64_t B, int64_t D, const int32
                  cudaStream_t st) {
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) |
                                      reinterpret_cast<uintptr_t>(dF) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0;
-  const int per_thread = vec ? 4 : 1;
-  int threads = 64;
-  while (threads < 256 && threads * per_thread * 2 <= D) threads *= 2;
+  const unsigned grid = (unsigned)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA);
+  const int threads = 32 * jsd::INDEX_ROWS_PER_CTA;
   if (vec)
-    jsd::jsd_index_kernel<T, 4><<<(unsigned)B, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr,
-                                                               iidx, t_dev, coefp, partials, (T*)dF, (T*)dG);
+    jsd::jsd_index_kernel<T, 4><<<grid, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr, iidx,
+                                                          t_dev, coefp, partials, (T*)dF, (T*)dG);
   else
-    jsd::jsd_index_kernel<T, 1><<<(unsigned)B, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr,
-                                                               iidx, t_dev, coefp, partials, (T*)dF, (T*)dG);
+    jsd::jsd_index_kernel<T, 1><<<grid, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr, iidx,
+                                                          t_dev, coefp, partials, (T*)dF, (T*)dG);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -214,7 +216,7 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
 
 extern "C" {
 
-int jsd_abi_version(void) { return 4; }
+int jsd_abi_version(void) { return 5; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -237,7 +239,8 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
                                                dG, st)));
   }();
   if (rc) return rc;
-  jsd::finalize_kernel<<<1, 256, 0, st>>>(partials, (int)B, 3, 1.0 / (double)B, 1.0 / (double)B, 1.0, 0.0, out4,
+  jsd::finalize_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>(
+      partials, (int)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA), 3, 1.0 / (double)B, 1.0 / (double)B, 1.0, 0.0, out4,
                                           loss_out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -295,7 +298,7 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
     return rc;
   const double inv_pos = 1.0 / (double)M;
   const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
-  jsd::finalize_dense_kernel<<<1, 256, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS, inv_pos, inv_neg,
+  jsd::finalize_dense_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS, inv_pos, inv_neg,
                                                 t_dev, out4, loss_out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -363,7 +366,7 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
 
 int jsd_sum_f32(const float* x, int64_t n, float* out, jsd_stream_t stream) {
   JSD_REQUIRE(x && out && fits_int(n), "jsd_sum_f32: bad argument");
-  jsd::sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, (int)n, out);
+  jsd::sum_kernel<<<1, jsd::FINALIZE_THREADS, 0, (cudaStream_t)stream>>>(x, (int)n, out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -388,6 +391,24 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
   if (int rc = jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, stream))
     return rc;
   return jsd_sum_f32(rowdot, B, dt_out, stream);     // gamma * dL/dt = sum_i <u_i, dU_i>
+}
+
+int jsd_normalize_cast_pair(const void* F, const void* G, int dtype, int64_t rows, int64_t D, void* U, void* V,
+                            float* inv_f, float* inv_g, jsd_stream_t stream) {
+  if (int rc = jsd_normalize_cast(F, dtype, rows, D, U, inv_f, stream)) return rc;
+  return jsd_normalize_cast(G, dtype, rows, D, V, inv_g, stream);
+}
+
+int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N, int64_t D, int64_t row_offset,
+                                  const void* V_all, const float* inv_f, const void* Gmat, int64_t ldg,
+                                  const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
+                                  float* rowdot, void* dF, float* dt_out, jsd_stream_t stream) {
+  JSD_REQUIRE(acc_u && rowdot && dt_out, "jsd_dense_backward_image_side: null pointer argument");
+  if (int rc = jsd_dense_bwd_du(Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
+  if (int rc = jsd_normalize_bwd(F, dtype, M, D, inv_f, acc_u, V_all, row_offset, gdiag, t_dev, gamma_dev, M, dF,
+                                 rowdot, stream))
+    return rc;
+  return jsd_sum_f32(rowdot, M, dt_out, stream);
 }
 
 int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,

@@ -111,39 +111,58 @@ __device__ __forceinline__ void neg_terms(float s, float tau_l2, float& d, float
 
 // Work iterator shared by the three roles: yields (tile, k_begin, k_end) segments.
 //
-// Stream-K is applied per GROUP of num_n_blocks CTAs: the (m-block, k-chunk) space is cut into one
-// contiguous range per group and CTA j of a group owns column block j, so the CTAs of a group walk
-// the same A tiles at the same time (the A operand is shared through L2 exactly as in the
-// whole-tile schedule) and every column block of an m-block is split at the same k.
+// Stream-K (opt-in, GRAD) follows the hybrid schedule of the Stream-K paper, applied per GROUP of
+// num_n_blocks workers (worker j of a group owns column block j, so a group walks the same A tiles in
+// lock step and the A operand is shared through L2 exactly as in the whole-tile schedule):
+//   1. the m-blocks that do not fill a whole wave of groups ("sk_mb" of them) are cut, as one
+//      (m-block, k-chunk) unit space, into one contiguous range per group -- every group gets the same
+//      fraction of a tile, a tile split between groups is finished by the group holding its head;
+//   2. the remaining m-blocks are whole tiles, one wave after the other.
 struct SegmentIter {
   int num_k, num_tiles, stride, tile;   // round-robin whole tiles
-  int n_blocks, n_blk;                  // stream-K: column blocks per m-block, this CTA's column block
-  long long u, u_end;                   // stream-K: (m-block, k-chunk) unit range of this CTA's group
+  int n_blocks, n_blk;                  // stream-K: column blocks per m-block, this worker's column block
+  int groups, group, sk_mb, dp_i, dp_waves;
+  long long u, u_end;                   // stream-K: unit range of this worker's group in the sk_mb space
   bool stream_k;
-  __device__ SegmentIter(bool sk, int cta, int grid, int tiles, int nk, int nb)
-      : num_k(nk), num_tiles(tiles), stride(grid), tile(cta), n_blocks(nb), n_blk(0), u(0), u_end(0), stream_k(sk) {
+  __device__ SegmentIter(bool sk, int worker, int n_workers, int tiles, int nk, int nb)
+      : num_k(nk), num_tiles(tiles), stride(n_workers), tile(worker), n_blocks(nb), n_blk(0), groups(1), group(0),
+        sk_mb(0), dp_i(0), dp_waves(0), u(0), u_end(0), stream_k(sk) {
     if (sk) {
-      const int groups = grid / nb, group = cta / nb;
-      n_blk = cta - group * nb;
-      const long long total = (long long)(tiles / nb) * nk;
-      u = total * group / groups;
-      u_end = total * (group + 1) / groups;
+      groups = n_workers / nb;
+      group = worker / nb;
+      n_blk = worker - group * nb;
+      const int num_mb = tiles / nb;
+      dp_waves = num_mb / groups;
+      sk_mb = num_mb - dp_waves * groups;
+      u = group_begin(worker, n_workers, tiles, nk, nb);
+      u_end = group_begin(worker + nb, n_workers, tiles, nk, nb);
     }
   }
-  // first unit of the range of the group `cta` belongs to
-  __device__ static long long group_begin(int cta, int grid, int tiles, int nk, int nb) {
-    return (long long)(tiles / nb) * nk * (cta / nb) / (grid / nb);
+  // first stream-K unit of the group `worker` belongs to (== total for the group past the last)
+  __device__ static long long group_begin(int worker, int n_workers, int tiles, int nk, int nb) {
+    const int groups = n_workers / nb, num_mb = tiles / nb;
+    const int sk = num_mb - (num_mb / groups) * groups;
+    return (long long)sk * nk * (worker / nb) / groups;
   }
   __device__ bool next(int& t, int& k0, int& k1) {
     if (stream_k) {
-      if (u >= u_end) return false;
-      const int m_blk = (int)(u / num_k);
-      t = m_blk * n_blocks + n_blk;       // n-fastest tile numbering
-      k0 = (int)(u - (long long)m_blk * num_k);
-      const long long rem = u_end - u;
-      k1 = (k0 + rem < num_k) ? (int)(k0 + rem) : num_k;
-      u += k1 - k0;
-      return true;
+      if (u < u_end) {
+        const int m_blk = (int)(u / num_k);
+        t = m_blk * n_blocks + n_blk;       // n-fastest tile numbering
+        k0 = (int)(u - (long long)m_blk * num_k);
+        const long long rem = u_end - u;
+        k1 = (k0 + rem < num_k) ? (int)(k0 + rem) : num_k;
+        u += k1 - k0;
+        return true;
+      }
+      if (dp_i < dp_waves) {
+        t = (sk_mb + group + dp_i * groups) * n_blocks + n_blk;
+        k0 = 0;
+        k1 = num_k;
+        ++dp_i;
+        return true;
+      }
+      return false;
     }
     if (tile >= num_tiles) return false;
     t = tile;
@@ -357,7 +376,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const long long m_end = (long long)(tile / num_n_blocks + 1) * num_k;   // end of this m-block's units
         while (sk_last + sk_step < (int)gridDim.x &&
                SegmentIter::group_begin((sk_last + sk_step) / CG, n_workers, num_tiles, num_k, num_n_blocks) < m_end)
-          sk_last += sk_step;
+          sk_last += sk_step;               // group_begin counts units of the stream-K m-blocks only
         if (lane == 0) {
           for (int c = cta + sk_step; c <= sk_last; c += sk_step) {
             const int* flag = p.sk_flags + c * NUM_EPI_WARPS + ew;

@@ -75,7 +75,8 @@ __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2hal
 template <typename T, int VEC, typename Fn>
 __device__ __forceinline__ void for_row(int D, int tid, int nthreads, Fn fn) {
   if constexpr (VEC == 4) {
-    for (int d = tid * 4; d < D; d += nthreads * 4) fn(d);
+#pragma unroll 2
+    for (int d = tid * 4; d < D; d += nthreads * 4) fn(d);   // two iterations of loads in flight per lane
   } else {
     for (int d = tid; d < D; d += nthreads) fn(d);
   }
@@ -105,102 +106,132 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 
 // ------------------------------------------------------------------ index mode
-// One CTA per row j.  Computes everything row j of dF and dG needs:
-//   positive pair (j, j), row j's negative (j, n = neg[j]) and the pairs (p, j)
-//   of every row p whose negative is j (CSR inverse; NULL => p = j-1, the
-//   roll-by-one of loss.py:214-216).
+// One WARP per row j, eight consecutive rows per CTA (a row's negative and pre-image are usually its
+// neighbours, so their data is found in L1).  The warp computes everything row j of dF and dG needs:
+//   the positive pair (j, j), row j's negative (j, n = neg[j]) and the pairs (p, j) of every row p
+//   whose negative is j (CSR inverse; NULL => p = j-1, the roll-by-one of loss.py:214-216).
+// No block barriers: all reductions are warp shuffles.  Pass 1 accumulates the dot products, pass 2
+// re-reads the (L1-resident) rows and writes both gradients, with <u,dU> and <v,dV> in closed form.
+constexpr int INDEX_ROWS_PER_CTA = 8;
+
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * INDEX_ROWS_PER_CTA)
 jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D, const int* __restrict__ neg_index,
                  const int* __restrict__ inv_ptr, const int* __restrict__ inv_idx, const float* __restrict__ t_dev,
                  float* __restrict__ coefp, float* __restrict__ partials, T* __restrict__ dF, T* __restrict__ dG) {
-  __shared__ float scratch[5 * 32];
-  const int j = blockIdx.x;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ float cta_part[INDEX_ROWS_PER_CTA][3];
+  const int lane = threadIdx.x & 31;
+  const int wrow = threadIdx.x >> 5;
+  const int j = blockIdx.x * INDEX_ROWS_PER_CTA + wrow;
+  if (lane < 3) cta_part[wrow][lane] = 0.f;
+  if (j < B) {
   const int n = neg_index ? neg_index[j] : (j + 1 == B ? 0 : j + 1);
   const float tau = expf(*t_dev);
   const float invB = 1.f / (float)B;
   const T* fj = F + (size_t)j * D;
   const T* gj = G + (size_t)j * D;
   const T* gn = G + (size_t)n * D;
+  // rows p that use text row j as their negative
+  const int pbeg = inv_ptr ? inv_ptr[j] : 0;
+  const int pend = inv_ptr ? inv_ptr[j + 1] : 1;
+  const int p0 = inv_idx ? (pbeg < pend ? inv_idx[pbeg] : 0) : (j == 0 ? B - 1 : j - 1);
+  const bool one_pre = (pend - pbeg == 1);          // permutation (normal / cluster mode): fully fused path
+  const T* fp0 = F + (size_t)p0 * D;
 
-  float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // ff, gg, fg, gngn, fgn
-  for_row<T, VEC>(D, tid, nt, [&](int d) {
+  float s7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // ff, gg, fg, gngn, f.gn, fpfp, fp.g
+  for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
       const float4 f = Vec4<T>::load(fj + d), g = Vec4<T>::load(gj + d), h = Vec4<T>::load(gn + d);
-      s5[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
-      s5[1] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
-      s5[2] += f.x * g.x + f.y * g.y + f.z * g.z + f.w * g.w;
-      s5[3] += h.x * h.x + h.y * h.y + h.z * h.z + h.w * h.w;
-      s5[4] += f.x * h.x + f.y * h.y + f.z * h.z + f.w * h.w;
+      s7[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+      s7[1] += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+      s7[2] += f.x * g.x + f.y * g.y + f.z * g.z + f.w * g.w;
+      s7[3] += h.x * h.x + h.y * h.y + h.z * h.z + h.w * h.w;
+      s7[4] += f.x * h.x + f.y * h.y + f.z * h.z + f.w * h.w;
+      if (one_pre) {
+        const float4 q = Vec4<T>::load(fp0 + d);
+        s7[5] += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+        s7[6] += q.x * g.x + q.y * g.y + q.z * g.z + q.w * g.w;
+      }
     } else {
       const float f = to_f32(fj[d]), g = to_f32(gj[d]), h = to_f32(gn[d]);
-      s5[0] += f * f;
-      s5[1] += g * g;
-      s5[2] += f * g;
-      s5[3] += h * h;
-      s5[4] += f * h;
+      s7[0] += f * f;
+      s7[1] += g * g;
+      s7[2] += f * g;
+      s7[3] += h * h;
+      s7[4] += f * h;
+      if (one_pre) {
+        const float q = to_f32(fp0[d]);
+        s7[5] += q * q;
+        s7[6] += q * g;
+      }
     }
   });
-  block_sum<5>(s5, scratch);
-  const float inv_f = 1.f / fmaxf(sqrtf(s5[0]), kNormEps);
-  const float inv_g = 1.f / fmaxf(sqrtf(s5[1]), kNormEps);
-  const float inv_gn = 1.f / fmaxf(sqrtf(s5[3]), kNormEps);
-  const float s_pos = tau * s5[2] * inv_f * inv_g;
-  const float s_neg = tau * s5[4] * inv_f * inv_gn;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) s7[i] = warp_sum(s7[i]);
+  const float inv_f = 1.f / fmaxf(sqrtf(s7[0]), kNormEps);
+  const float inv_g = 1.f / fmaxf(sqrtf(s7[1]), kNormEps);
+  const float inv_gn = 1.f / fmaxf(sqrtf(s7[3]), kNormEps);
+  const float s_pos = tau * s7[2] * inv_f * inv_g;
+  const float s_neg = tau * s7[4] * inv_f * inv_gn;
   const float a = -sigmoid_f(-s_pos) * invB;   // dL/ds_pos
   const float b = sigmoid_f(s_neg) * invB;     // dL/ds_neg
   const float udot = a * s_pos + b * s_neg;    // <u_j, dU_j>
-
-  // rows p that use text row j as their negative
-  int pbeg, pend;
-  if (inv_ptr) {
-    pbeg = inv_ptr[j];
-    pend = inv_ptr[j + 1];
-  } else {
-    pbeg = 0;
-    pend = 1;
-  }
-  float vdot = a * s_pos;   // <v_j, dV_j>
-  for (int k = pbeg; k < pend; ++k) {
-    const int pr = inv_idx ? inv_idx[k] : (j == 0 ? B - 1 : j - 1);
-    const T* fp = F + (size_t)pr * D;
-    float s2[2] = {0.f, 0.f};   // fpfp, fp.gj
-    for_row<T, VEC>(D, tid, nt, [&](int d) {
-      if constexpr (VEC == 4) {
-        const float4 f = Vec4<T>::load(fp + d), g = Vec4<T>::load(gj + d);
-        s2[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
-        s2[1] += f.x * g.x + f.y * g.y + f.z * g.z + f.w * g.w;
-      } else {
-        const float f = to_f32(fp[d]), g = to_f32(gj[d]);
-        s2[0] += f * f;
-        s2[1] += f * g;
-      }
-    });
-    block_sum<2>(s2, scratch);
-    const float inv_fp = 1.f / fmaxf(sqrtf(s2[0]), kNormEps);
-    const float sp = tau * s2[1] * inv_fp * inv_g;
+  float vdot = a * s_pos;                      // <v_j, dV_j>
+  float c0 = 0.f;                              // tau * b_p / ||f_p|| of the single pre-image
+  if (one_pre) {
+    const float inv_fp = 1.f / fmaxf(sqrtf(s7[5]), kNormEps);
+    const float sp = tau * s7[6] * inv_fp * inv_g;
     const float bp = sigmoid_f(sp) * invB;
     vdot += bp * sp;
-    if (tid == 0) coefp[pr] = tau * bp * inv_fp;   // each p has exactly one target row => no race
+    c0 = tau * bp * inv_fp;
+  } else {
+    // general index (a text row may be the negative of any number of rows): one extra sweep per pre-image
+    for (int k = pbeg; k < pend; ++k) {
+      const int pr = inv_idx[k];
+      const T* fp = F + (size_t)pr * D;
+      float s2[2] = {0.f, 0.f};   // fpfp, fp.gj
+      for_row<T, VEC>(D, lane, 32, [&](int d) {
+        if constexpr (VEC == 4) {
+          const float4 f = Vec4<T>::load(fp + d), g = Vec4<T>::load(gj + d);
+          s2[0] += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+          s2[1] += f.x * g.x + f.y * g.y + f.z * g.z + f.w * g.w;
+        } else {
+          const float f = to_f32(fp[d]), g = to_f32(gj[d]);
+          s2[0] += f * f;
+          s2[1] += f * g;
+        }
+      });
+      s2[0] = warp_sum(s2[0]);
+      s2[1] = warp_sum(s2[1]);
+      const float inv_fp = 1.f / fmaxf(sqrtf(s2[0]), kNormEps);
+      const float sp = tau * s2[1] * inv_fp * inv_g;
+      const float bp = sigmoid_f(sp) * invB;
+      vdot += bp * sp;
+      if (lane == 0) coefp[pr] = tau * bp * inv_fp;   // each p has exactly one target row => no race
+    }
+    __syncwarp();
   }
-  __syncthreads();
 
   T* dfj = dF + (size_t)j * D;
   T* dgj = dG + (size_t)j * D;
   const float ca = tau * a, cb = tau * b;
-  for_row<T, VEC>(D, tid, nt, [&](int d) {
+  for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
       const float4 f = Vec4<T>::load(fj + d), g = Vec4<T>::load(gj + d), h = Vec4<T>::load(gn + d);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = pbeg; k < pend; ++k) {
-        const int pr = inv_idx ? inv_idx[k] : (j == 0 ? B - 1 : j - 1);
-        const float c = coefp[pr];
-        const float4 q = Vec4<T>::load(F + (size_t)pr * D + d);
-        acc.x = fmaf(c, q.x, acc.x);
-        acc.y = fmaf(c, q.y, acc.y);
-        acc.z = fmaf(c, q.z, acc.z);
-        acc.w = fmaf(c, q.w, acc.w);
+      if (one_pre) {
+        const float4 q = Vec4<T>::load(fp0 + d);
+        acc = make_float4(c0 * q.x, c0 * q.y, c0 * q.z, c0 * q.w);
+      } else {
+        for (int k = pbeg; k < pend; ++k) {
+          const int pr = inv_idx[k];
+          const float c = coefp[pr];
+          const float4 q = Vec4<T>::load(F + (size_t)pr * D + d);
+          acc.x = fmaf(c, q.x, acc.x);
+          acc.y = fmaf(c, q.y, acc.y);
+          acc.z = fmaf(c, q.z, acc.z);
+          acc.w = fmaf(c, q.w, acc.w);
+        }
       }
       float4 of, og;
 #define JSD_IDX_ELT(c)                                                            \
@@ -216,33 +247,48 @@ jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D,
     } else {
       const float f = to_f32(fj[d]), g = to_f32(gj[d]), h = to_f32(gn[d]);
       float acc = 0.f;
-      for (int k = pbeg; k < pend; ++k) {
-        const int pr = inv_idx ? inv_idx[k] : (j == 0 ? B - 1 : j - 1);
-        acc = fmaf(coefp[pr], to_f32(F[(size_t)pr * D + d]), acc);
+      if (one_pre) {
+        acc = c0 * to_f32(fp0[d]);
+      } else {
+        for (int k = pbeg; k < pend; ++k) {
+          const int pr = inv_idx[k];
+          acc = fmaf(coefp[pr], to_f32(F[(size_t)pr * D + d]), acc);
+        }
       }
       const float u = f * inv_f, v = g * inv_g, vn = h * inv_gn;
       dfj[d] = from_f32<T>((ca * v + cb * vn - u * udot) * inv_f);
       dgj[d] = from_f32<T>((ca * u + acc - v * vdot) * inv_g);
     }
   });
-  if (tid == 0) {
-    partials[3 * (size_t)j + 0] = softplus_f(-s_pos);
-    partials[3 * (size_t)j + 1] = softplus_f(s_neg);
-    partials[3 * (size_t)j + 2] = udot;
+  __syncwarp();
+  if (lane == 0) {
+    cta_part[wrow][0] = softplus_f(-s_pos);
+    cta_part[wrow][1] = softplus_f(s_neg);
+    cta_part[wrow][2] = udot;
+  }
+  }  // j < B
+  __syncthreads();
+  if (threadIdx.x < 3) {   // fixed-order sum over the CTA's rows: one partial triple per CTA
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < INDEX_ROWS_PER_CTA; ++w) acc += cta_part[w][threadIdx.x];
+    partials[3 * (size_t)blockIdx.x + threadIdx.x] = acc;
   }
 }
 
 // out4 = {pos, neg, pos + neg, dL/dt} (+ an optional separate copy of the loss); deterministic (fixed order, fp64).
-__global__ void __launch_bounds__(256)
+constexpr int FINALIZE_THREADS = 1024;
+
+__global__ void __launch_bounds__(FINALIZE_THREADS)
 finalize_kernel(const float* __restrict__ partials, int n, int width, double inv0, double inv1, double inv2,
                 double inv3, float* __restrict__ out4, float* __restrict__ loss_out) {
-  __shared__ double sh[4][256];
+  __shared__ double sh[4][FINALIZE_THREADS];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += 256)
+  for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS)
     for (int k = 0; k < width; ++k) acc[k] += (double)partials[(size_t)i * width + k];
   for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = acc[k];
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = FINALIZE_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s)
       for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
     __syncthreads();
@@ -342,16 +388,16 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
 // Dense-mode loss: partials rows = {sum softplus(-x_pos), sum max(s, 0), sum log2(1 + e), -} per epilogue warp.
 //   pos = P0 / M,   neg = (tau * P1 + ln2 * P2) / (M (N - 1)),   out4 = {pos, neg, pos + neg, 0}
 // (dL/dt of the dense mode is produced by the backward: it is the sum of the row dots <u_i, dU_i>.)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FINALIZE_THREADS)
 finalize_dense_kernel(const float* __restrict__ partials, int n, double inv_pos, double inv_neg,
                       const float* __restrict__ t_dev, float* __restrict__ out4, float* __restrict__ loss_out) {
-  __shared__ double sh[3][256];
+  __shared__ double sh[3][FINALIZE_THREADS];
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += 256)
+  for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS)
     for (int k = 0; k < 3; ++k) acc[k] += (double)partials[(size_t)i * 4 + k];
   for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = acc[k];
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = FINALIZE_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s)
       for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
     __syncthreads();
@@ -369,14 +415,14 @@ finalize_dense_kernel(const float* __restrict__ partials, int n, double inv_pos,
 }
 
 // out = scale_dev * sum(x[0..n)) in a fixed order (fp64): dL/dt = sum_i <u_i, dU_i> of the dense backward
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FINALIZE_THREADS)
 sum_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
-  __shared__ double sh[256];
+  __shared__ double sh[FINALIZE_THREADS];
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) acc += (double)x[i];
+  for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS) acc += (double)x[i];
   sh[threadIdx.x] = acc;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = FINALIZE_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
     __syncthreads();
   }

@@ -258,6 +258,36 @@ def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, pa
     return (dx, rowdot[rows]) if want_dt else dx
 
 
+def normalize_cast_pair(f: torch.Tensor, g: torch.Tensor):
+    """(U, V, inv_f, inv_g) for two [rows, D] tensors of the same dtype in one library call."""
+    rows, d = f.shape
+    dev = f.device
+    uv = torch.empty(2, rows, d, dtype=torch.bfloat16, device=dev)
+    inv = torch.empty(2, rows, dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        _lib.call("jsd_normalize_cast_pair", f.data_ptr(), g.data_ptr(), _code(f), rows, d, uv[0].data_ptr(),
+                  uv[1].data_ptr(), inv[0].data_ptr(), inv[1].data_ptr(), _stream())
+    return uv[0], uv[1], inv[0], inv[1]
+
+
+def dense_backward_image_side(f, v_all, inv_f, gmat, gdiag, t, gamma, row_offset: int):
+    """dU GEMM + positive-pair term + normalisation Jacobian + dL/dt for a row slab, one library call.
+    Returns (dF, dt) with dt = gamma * dL_r/dt."""
+    m, d = f.shape
+    n = v_all.shape[0]
+    dev = f.device
+    tt = _scalar(t, "temperature")
+    gg = _scalar(gamma, "gamma")
+    acc = torch.empty(m, d, dtype=torch.float32, device=dev)
+    small = torch.empty(m + 1, dtype=torch.float32, device=dev)
+    df = torch.empty_like(f)
+    with _on_device(dev):
+        _lib.call("jsd_dense_backward_image_side", f.data_ptr(), _code(f), m, n, d, row_offset, v_all.data_ptr(),
+                  inv_f.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(), tt.data_ptr(), gg.data_ptr(),
+                  acc.data_ptr(), small.data_ptr(), df.data_ptr(), small[m:].data_ptr(), _stream())
+    return df, small[m]
+
+
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn_major: bool = False, b_mn_major: bool = False,
               stream_k: bool = True) -> torch.Tensor:
     """C [M, N] fp32 = A . B^T on the tcgen05 kernel.  a is [M, K] (K-major) or, with a_mn_major,

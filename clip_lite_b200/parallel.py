@@ -40,12 +40,6 @@ def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
     return out
 
 
-def _reduce_scatter_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
-    out = torch.empty(x.shape[0] // world, x.shape[1], dtype=x.dtype, device=x.device)
-    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=group)
-    return out
-
-
 class _GatheredDenseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f, g, t, group):
@@ -57,8 +51,7 @@ class _GatheredDenseFn(torch.autograd.Function):
         with torch.autocast(f.device.type, enabled=False):
             dt = torch.promote_types(f.dtype, g.dtype)
             fc, gc = f.to(dt).contiguous(), g.to(dt).contiguous()
-            u, inv_f = K.normalize_cast(fc)
-            v, inv_g = K.normalize_cast(gc)
+            u, v, inv_f, inv_g = K.normalize_cast_pair(fc, gc)
             v_all = _all_gather_rows(v, world, group) if world > 1 else v
             out4, loss, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
         if need_grad:
@@ -74,12 +67,19 @@ class _GatheredDenseFn(torch.autograd.Function):
         m, n = fc.shape[0], v_all.shape[0]
         with torch.autocast(fc.device.type, enabled=False):
             gamma = grad_loss.float()
-            # text side first so that its reduce-scatter is in flight during the image side
+            # text side first: its reduce-scatter runs on NCCL's stream while the image side computes
             dv_partial = K.dense_bwd_dv(gmat, u, n, t, gamma)                  # [N, D], partial over ranks
-            dv = _reduce_scatter_rows(dv_partial, ctx.world, ctx.group) if ctx.world > 1 else dv_partial
-            du = K.dense_bwd_du(gmat, v_all, t, gamma)                         # [M, D], complete
-            # dL_r/dt falls out of the image side: sum_i <u_i, dU_i> (dU_i is complete on this rank)
-            df, dt = K.normalize_bwd(fc, inv_f, du, v_all, ctx.rank * m, gdiag, t, gamma, m, want_dt=True)
+            work = None
+            if ctx.world > 1:
+                dv = torch.empty(m, dv_partial.shape[1], dtype=dv_partial.dtype, device=dv_partial.device)
+                work = dist.reduce_scatter_tensor(dv, dv_partial, op=dist.ReduceOp.SUM, group=ctx.group,
+                                                  async_op=True)
+            else:
+                dv = dv_partial
+            # image side: dU_r is complete on this rank; dL_r/dt = sum_i <u_i, dU_i> falls out of it
+            df, dt = K.dense_backward_image_side(fc, v_all, inv_f, gmat, gdiag, t, gamma, ctx.rank * m)
+            if work is not None:
+                work.wait()                                                    # compute stream waits for the reduction
             dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, m)
         fd, gd, td = ctx.dtypes
         return df.to(fd), dg.to(gd), dt.to(td), None

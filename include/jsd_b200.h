@@ -128,6 +128,17 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
                        const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v,
                        float* rowdot, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
+/* Row-slab (multi-GPU) convenience calls: one FFI crossing each.
+ *   jsd_normalize_cast_pair       = jsd_normalize_cast(F) , jsd_normalize_cast(G)
+ *   jsd_dense_backward_image_side = jsd_dense_bwd_du, jsd_normalize_bwd (positives at column row_offset + i of
+ *                                   V_all, row dots), dt_out = jsd_sum_f32(rowdot) = gamma * dL_r/dt */
+int jsd_normalize_cast_pair(const void* F, const void* G, int dtype, int64_t rows, int64_t D, void* U_bf16,
+                            void* V_bf16, float* inv_f, float* inv_g, jsd_stream_t stream);
+int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N, int64_t D, int64_t row_offset,
+                                  const void* V_all_bf16, const float* inv_f, const void* Gmat_bf16, int64_t ldg,
+                                  const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
+                                  float* rowdot, void* dF, float* dt_out, jsd_stream_t stream);
+
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or
  * B^T [K, ldb] (b_mn_major = 1).  sk_workspace as above (NULL => whole tiles only).

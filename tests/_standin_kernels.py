@@ -52,3 +52,14 @@ def normalize_bwd(x, inv_norm, acc, partner, partner_offset, gdiag, t, gamma, m_
     u = x.double() * inv
     dx = ((d - u * (u * d).sum(-1, keepdim=True)) * inv).to(x.dtype)
     return (dx, (u * d).sum().float()) if want_dt else dx
+
+
+def normalize_cast_pair(f, g):
+    u, inv_f = normalize_cast(f)
+    v, inv_g = normalize_cast(g)
+    return u, v, inv_f, inv_g
+
+
+def dense_backward_image_side(f, v_all, inv_f, gmat, gdiag, t, gamma, row_offset):
+    du = dense_bwd_du(gmat, v_all, t, gamma)
+    return normalize_bwd(f, inv_f, du, v_all, row_offset, gdiag, t, gamma, f.shape[0], want_dt=True)

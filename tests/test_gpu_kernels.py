@@ -278,3 +278,20 @@ def test_fused_forward_backward_calls_equal_the_staged_calls(K, dtype):
     assert torch.equal(df, dfb) and torch.equal(dg, dgb) and torch.equal(dt, dtb)
     _, _, rdt = orc.jsd_dense_grads(f.double(), g.double(), T0, gamma=0.7)
     assert relerr(dt, rdt) < GRAD_RTOL
+
+
+def test_slab_convenience_calls_equal_the_staged_calls(K):
+    m, n, d, off = 256, 1024, 128, 512
+    f, g = orc.synth_embeddings(n, d, seed=6, correlated=True)
+    f, g = f.cuda(), g.cuda()
+    t = dev_t()
+    gamma = torch.tensor(0.5, device="cuda")
+    u_all, v_all, inv_f_all, inv_g_all = K.normalize_cast_pair(f, g)
+    u2, inv2 = K.normalize_cast(f)
+    assert torch.equal(u_all, u2) and torch.equal(inv_f_all, inv2)
+    fl, u, inv_f = f[off:off + m].contiguous(), u_all[off:off + m].contiguous(), inv_f_all[off:off + m].contiguous()
+    _, _, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=off)
+    df, dt = K.dense_backward_image_side(fl, v_all, inv_f, gmat, gdiag, t, gamma, off)
+    du = K.dense_bwd_du(gmat, v_all, t, gamma)
+    dfb, dtb = K.normalize_bwd(fl, inv_f, du, v_all, off, gdiag, t, gamma, m, want_dt=True)
+    assert torch.equal(df, dfb) and torch.equal(dt, dtb)

@@ -73,7 +73,7 @@ def main():
         print(f"  {'torch.matmul U@V.T bf16':24s} median {med*1e3:9.1f} us   min {mn*1e3:9.1f} us  {flops/(med*1e-3)/1e12:8.1f} TFLOP/s")
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "gemm"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("gemm", "index")):
     main()
 
 
@@ -98,3 +98,27 @@ def gemm_variants():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "gemm":
     gemm_variants()
+
+
+def index_mode():
+    """Reference-semantics (index) kernel vs the HBM roofline."""
+    for b, d, dt in ((8192, 2048, torch.float32), (8192, 2048, torch.bfloat16), (1024, 2048, torch.float32), (65536, 512, torch.bfloat16)):
+        f = torch.randn(b, d, device="cuda").to(dt)
+        g = torch.randn(b, d, device="cuda").to(dt)
+        t = torch.tensor(2.6593, device="cuda")
+        for _ in range(3):
+            K.index_fwd_bwd(f, g, t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):                      # back to back: device throughput, host overhead amortised
+            K.index_fwd_bwd(f, g, t)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        nbytes = 4.0 * b * d * f.element_size()
+        print(f"  index B={b} D={d} {str(dt):15s} {us:8.1f} us/call (incl. finalize)  {nbytes/(us*1e-6)/1e9:8.1f} GB/s algorithmic")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "index":
+    index_mode()

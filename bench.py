@@ -216,9 +216,21 @@ def run_b200(args, wl):
             return parallel.gathered_dense_loss(f, g, t_dev)[0]
         return ops.jsd_dense_loss(f, g, t_dev)[0]
 
-    def step():
+    def eager_step():
         loss = loss_fn(f_dev, g_dev)
         return (loss,) + torch.autograd.grad(loss, (f_dev, g_dev, t_dev))
+
+    # The step is a fixed kernel sequence: replay it as one CUDA graph (clip_lite_b200.graph.GraphedStep)
+    # unless --cuda-graph 0; the eager autograd path is what the e2e leg below measures.
+    step, graphed = eager_step, False
+    if args.cuda_graph:
+        try:
+            from clip_lite_b200.graph import GraphedStep
+            gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
+            step, graphed = gs, True
+        except Exception as exc:                      # capture not possible here: fall back to eager launches
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -357,7 +369,7 @@ def run_b200(args, wl):
             "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "rows_per_gpu": rows,
-                       "neg_mode": "dense", "parallelism": f"dp{world}",
+                       "neg_mode": "dense", "parallelism": f"dp{world}", "cuda_graph": graphed,
                        "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
                        "inputs": "bf16 unit rows resident in HBM; N(0,1) features, text = 0.6 img + 0.8 noise"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
@@ -379,6 +391,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="dense_b8192_d1024")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="replay the step as one CUDA graph (default 1)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -223,3 +223,18 @@ def test_full_size_index_mode_vs_oracle(ops):
     rdf, rdg, rdt = orc.jsd_index_grads(f.cuda().double(), g.cuda().double(), orc.T_INIT)
     assert relerr(loss, ref["loss"]) < 1e-5
     assert relerr(fl.grad, rdf) < 1e-4 and relerr(gl.grad, rdg) < 1e-4 and relerr(t.grad, rdt) < 1e-4
+
+
+def test_cuda_graph_replay_matches_eager(ops):
+    from clip_lite_b200.graph import GraphedStep
+    f, g = orc.synth_embeddings(512, 128, seed=7, correlated=True)
+    f, g = f.cuda(), g.cuda()
+    t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
+    gs = GraphedStep(lambda a, b, tt: ops.jsd_dense_loss(a, b, tt), f, g, t)
+    for seed in (7, 8):
+        f2, g2 = orc.synth_embeddings(512, 128, seed=seed, correlated=True)
+        loss, df, dg, dt = gs(f2.cuda(), g2.cuda())
+        fl, gl = f2.cuda().requires_grad_(True), g2.cuda().requires_grad_(True)
+        ref_loss, _ = ops.jsd_dense_loss(fl, gl, t)
+        rdf, rdg, rdt = torch.autograd.grad(ref_loss, (fl, gl, t))
+        assert torch.equal(loss, ref_loss) and torch.equal(df, rdf) and torch.equal(dg, rdg) and torch.equal(dt, rdt)

@@ -223,7 +223,7 @@ def run_b200(args, wl):
     # The step is a fixed kernel sequence: replay it as one CUDA graph (clip_lite_b200.graph.GraphedStep)
     # unless --cuda-graph 0; the eager autograd path is what the e2e leg below measures.
     step, graphed = eager_step, False
-    if args.cuda_graph:
+    if args.cuda_graph and world == 1:        # NCCL collectives are not captured: multi-GPU runs launch eagerly
         try:
             from clip_lite_b200.graph import GraphedStep
             gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
@@ -292,12 +292,15 @@ def run_b200(args, wl):
             if i + 1 < steps:
                 issue_h2d(slot ^ 1)
             main.wait_event(h2d_done[slot])
-            f = stage[slot][0].requires_grad_(True)
-            g = stage[slot][1].requires_grad_(True)
-            loss = loss_fn(f, g)
-            torch.autograd.grad(loss, (f, g, t_dev))
-            stage[slot][0].requires_grad_(False)
-            stage[slot][1].requires_grad_(False)
+            if graphed:
+                loss = step(stage[slot][0], stage[slot][1])[0]      # device copy into the graph's inputs + replay
+            else:
+                f = stage[slot][0].requires_grad_(True)
+                g = stage[slot][1].requires_grad_(True)
+                loss = loss_fn(f, g)
+                torch.autograd.grad(loss, (f, g, t_dev))
+                stage[slot][0].requires_grad_(False)
+                stage[slot][1].requires_grad_(False)
             consumed[slot].record(main)
             loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         end.record(main)

@@ -82,7 +82,7 @@ class ClockSampler:
     }
 
     def __init__(self, index):
-        self.samples, self.bits, self.max_mhz, self._stop = [], 0, None, threading.Event()
+        self.samples, self.power, self.bits, self.max_mhz, self._stop = [], [], 0, None, threading.Event()
         self._thr = None
         try:
             import pynvml
@@ -98,6 +98,7 @@ class ClockSampler:
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 try:
                     self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
@@ -120,7 +121,7 @@ class ClockSampler:
         s = sorted(self.samples)
         reasons = [n for b, n in self.REASONS.items() if self.bits & b and n != "gpu_idle"]
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(s)}
+                "samples": len(s), "power_w_max": (max(self.power) if self.power else None)}
 
 
 # ------------------------------------------------------------------ CPU (reference) arm

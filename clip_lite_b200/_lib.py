@@ -10,7 +10,10 @@ import ctypes
 import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
-from .build import LIB_PATH
+from .build import LIB_PATH as _DEFAULT_LIB_PATH
+
+# development aid: A/B-test an alternative build of the library
+LIB_PATH = os.environ.get("JSD_LIB", _DEFAULT_LIB_PATH)
 
 # name -> (restype, argtypes); mirrors include/jsd_b200.h one to one
 SIGNATURES = {

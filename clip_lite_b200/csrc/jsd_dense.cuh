@@ -415,7 +415,14 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
       }
 
-      mbar_wait(tfull_bar(acc), acc_phase);   // all lanes poll: measured 4 % faster than one polling lane + __syncwarp
+#ifndef JSD_GRAD_EPI_SLEEP_NS
+#define JSD_GRAD_EPI_SLEEP_NS 1000
+#endif
+      if constexpr (MODE == MODE_GRAD && JSD_GRAD_EPI_SLEEP_NS > 0) {
+        mbar_wait_relaxed(tfull_bar(acc), acc_phase, JSD_GRAD_EPI_SLEEP_NS);   // long wait: poll gently
+      } else {
+        mbar_wait(tfull_bar(acc), acc_phase);   // short waits: all lanes poll (4 % faster than one lane + __syncwarp)
+      }
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BLOCK_N + cgrp * COLS_PER_WARP + ((uint32_t)(32 * q) << 16);
 

@@ -68,6 +68,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same, for long waits (an epilogue warp waiting ~100 us for a 128-chunk accumulator): sleep between polls.
+// The chip runs at its power cap under these kernels, so 16 warps spinning at full rate cost clock.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if ((++spins & 0xFFu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- device-scope flags (stream-K hand-off)
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;

@@ -182,7 +182,10 @@ template <typename T>
 int launch_normalize(const void* X, int64_t rows, int64_t D, void* Xn, float* inv_norm, cudaStream_t st) {
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xn)) & 15) == 0;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (vec)
+  if (vec && D % 128 == 0 && D / 128 <= jsd::ROW_REG_CHUNKS)
+    jsd::normalize_cast_reg_kernel<T><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)(D / 128),
+                                                            (__nv_bfloat16*)Xn, inv_norm);
+  else if (vec)
     jsd::normalize_cast_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, (__nv_bfloat16*)Xn, inv_norm);
   else
     jsd::normalize_cast_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, (__nv_bfloat16*)Xn, inv_norm);
@@ -198,7 +201,11 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
                    ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(dX) | reinterpret_cast<uintptr_t>(acc) |
                      reinterpret_cast<uintptr_t>(partner)) & 15) == 0;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (vec)
+  if (vec && D % 128 == 0 && D / 128 <= jsd::ROW_REG_CHUNKS)
+    jsd::normalize_bwd_reg_kernel<T><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)(D / 128), inv_norm, acc,
+                                                           (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
+                                                           gamma_dev, inv_rows, (T*)dX, rowdot);
+  else if (vec)
     jsd::normalize_bwd_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
                                                         (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
                                                         gamma_dev, inv_rows, (T*)dX, rowdot);

@@ -385,6 +385,85 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
   });
 }
 
+// ------------------------------------------------------------------ register-resident variants (D = nch * 128 <= 1024)
+// Same arithmetic as the two kernels above, but every row is read from memory exactly once: a lane keeps
+// its (up to) 8 x 4 elements of each operand in registers between the reduction and the write-back, and all
+// loads of a row are in flight together.
+constexpr int ROW_REG_CHUNKS = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+normalize_cast_reg_kernel(const T* __restrict__ X, int rows, int nch, __nv_bfloat16* __restrict__ Xn,
+                          float* __restrict__ inv_norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int D = nch * 128;
+  const T* x = X + (size_t)row * D + lane * 4;
+  float4 xv[ROW_REG_CHUNKS];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+    if (i < nch) xv[i] = Vec4<T>::load(x + i * 128);
+#pragma unroll
+  for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+    if (i < nch) ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), kNormEps);
+  __nv_bfloat16* o = Xn + (size_t)row * D + lane * 4;
+#pragma unroll
+  for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+    if (i < nch)
+      Vec4<__nv_bfloat16>::store(o + i * 128, make_float4(xv[i].x * inv, xv[i].y * inv, xv[i].z * inv, xv[i].w * inv));
+  if (lane == 0) inv_norm[row] = inv;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+normalize_bwd_reg_kernel(const T* __restrict__ X, int rows, int nch, const float* __restrict__ inv_norm,
+                         const float* __restrict__ acc, const __nv_bfloat16* __restrict__ partner,
+                         long long partner_offset, const float* __restrict__ gdiag, const float* __restrict__ t_dev,
+                         const float* __restrict__ gamma_dev, float inv_rows, T* __restrict__ dX,
+                         float* __restrict__ rowdot) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int D = nch * 128;
+  const float gamma = gamma_dev ? *gamma_dev : 1.f;
+  const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
+  const float inv = inv_norm[row];
+  const T* x = X + (size_t)row * D + lane * 4;
+  const float* a = acc + (size_t)row * D + lane * 4;
+  const __nv_bfloat16* pr = partner + (size_t)(row + partner_offset) * D + lane * 4;
+  float4 xv[ROW_REG_CHUNKS], dv[ROW_REG_CHUNKS];
+#pragma unroll
+  for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+    if (i < nch) {
+      xv[i] = Vec4<T>::load(x + i * 128);
+      const float4 g = Vec4<float>::load(a + i * 128);
+      const float4 q = Vec4<__nv_bfloat16>::load(pr + i * 128);
+      dv[i] = make_float4(fmaf(c, q.x, g.x), fmaf(c, q.y, g.y), fmaf(c, q.z, g.z), fmaf(c, q.w, g.w));   // dU
+    }
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+    if (i < nch) dot += xv[i].x * dv[i].x + xv[i].y * dv[i].y + xv[i].z * dv[i].z + xv[i].w * dv[i].w;
+  dot = warp_sum(dot) * inv;   // <u, dU>
+  if (rowdot != nullptr && lane == 0) rowdot[row] = dot;
+  T* o = dX + (size_t)row * D + lane * 4;
+  const float k = inv * dot;
+#pragma unroll
+  for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+    if (i < nch) {
+      float4 r;
+      r.x = (dv[i].x - xv[i].x * k) * inv;
+      r.y = (dv[i].y - xv[i].y * k) * inv;
+      r.z = (dv[i].z - xv[i].z * k) * inv;
+      r.w = (dv[i].w - xv[i].w * k) * inv;
+      Vec4<T>::store(o + i * 128, r);
+    }
+}
+
 // Dense-mode loss: partials rows = {sum softplus(-x_pos), sum max(s, 0), sum log2(1 + e), -} per epilogue warp.
 //   pos = P0 / M,   neg = (tau * P1 + ln2 * P2) / (M (N - 1)),   out4 = {pos, neg, pos + neg, 0}
 // (dL/dt of the dense mode is produced by the backward: it is the sum of the row dots <u_i, dU_i>.)

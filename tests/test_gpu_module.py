@@ -238,3 +238,41 @@ def test_cuda_graph_replay_matches_eager(ops):
         ref_loss, _ = ops.jsd_dense_loss(fl, gl, t)
         rdf, rdg, rdt = torch.autograd.grad(ref_loss, (fl, gl, t))
         assert torch.equal(loss, ref_loss) and torch.equal(df, rdf) and torch.equal(dg, rdg) and torch.equal(dt, rdt)
+
+
+def test_stress_slab_65536_columns():
+    """BASELINE configs[3] shape per rank: an 8192-row slab against 65536 text rows, D = 512 (the 17 GB
+    fp32 score matrix is never formed; Gmat is 1 GB of bf16).  Checked against the oracle evaluated in
+    row blocks on the GPU, plus the gradient-orthogonality property."""
+    from clip_lite_b200 import kernels as K
+    m, n, d, off = 8192, 65536, 512, 3 * 8192
+    gen = torch.Generator("cuda").manual_seed(0)
+    g = torch.randn(n, d, device="cuda", generator=gen)
+    f = 0.6 * g[off:off + m] + 0.8 * torch.randn(m, d, device="cuda", generator=gen)
+    t = torch.tensor(orc.T_INIT, device="cuda")
+    gamma = torch.tensor(1.0, device="cuda")
+    u, _, inv_f, _ = K.normalize_cast_pair(f, g[off:off + m].contiguous())
+    v, inv_g = K.normalize_cast(g)
+    out4, loss, gmat, gdiag = K.dense_fwd(u, v, t, row_offset=off)
+    df, dt = K.dense_backward_image_side(f, v, inv_f, gmat, gdiag, t, gamma, off)
+    dv = K.dense_bwd_dv(gmat, u, n, t, gamma)
+    # oracle in fp64, 1024 rows at a time
+    pos = neg = 0.0
+    rdf = torch.empty(m, d, dtype=torch.float64, device="cuda")
+    rdv = torch.zeros(n, d, dtype=torch.float64, device="cuda")
+    un, vn = u.double(), v.double()
+    tau = float(np.exp(orc.T_INIT))
+    for r0 in range(0, m, 1024):
+        ref = orc.dense_from_unit(un[r0:r0 + 1024], vn, orc.T_INIT, row_offset=off + r0)
+        pos += float(ref["pos"]) * 1024 / m
+        neg += float(ref["neg"]) * 1024 / m
+        rdv += ref["dv_acc"] * (1024 / m)          # dense_from_unit scales by its own slab height
+        rdf[r0:r0 + 1024] = ref["du"] * (1024 / m)
+    assert relerr(out4[0], torch.tensor(pos)) < LOSS_RTOL and relerr(out4[1], torch.tensor(neg)) < LOSS_RTOL
+    assert relerr(dv, rdv) < GRAD_RTOL
+    # image-side gradient: project the fp64 dU through the normalisation and compare
+    uu = f.double() * inv_f.double()[:, None]
+    ref_df = (rdf - uu * (uu * rdf).sum(-1, keepdim=True)) * inv_f.double()[:, None]
+    assert relerr(df, ref_df) < GRAD_RTOL
+    assert float((f * df).sum(-1).abs().max()) < 1e-3 * float(df.abs().max() * f.norm(dim=-1).max())
+    assert torch.isfinite(dt)

@@ -224,10 +224,13 @@ def run_b200(args, wl):
     # The step is a fixed kernel sequence: replay it as one CUDA graph (clip_lite_b200.graph.GraphedStep)
     # unless --cuda-graph 0; the eager autograd path is what the e2e leg below measures.
     step, graphed = eager_step, False
-    if args.cuda_graph and world == 1:        # NCCL collectives are not captured: multi-GPU runs launch eagerly
+    if args.cuda_graph:
         try:
-            from clip_lite_b200.graph import GraphedStep
-            gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
+            if world == 1:
+                from clip_lite_b200.graph import GraphedStep
+                gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
+            else:      # NCCL is not captured: graph segments between the two eagerly launched collectives
+                gs = parallel.GraphedGatheredStep(f_dev, g_dev, t_dev)
             step, graphed = gs, True
         except Exception as exc:                      # capture not possible here: fall back to eager launches
             print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)

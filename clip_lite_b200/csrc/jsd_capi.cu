@@ -87,6 +87,21 @@ int sm_count_cached() {
 
 // CTA-group size of the tensor-core kernels: 2 (CTA pairs, 256x256 tiles) whenever there is more than
 // one 128-row block; JSD_CTA_GROUP=1|2 overrides (development / A-B timing).
+// development knob: JSD_TILE_ORDER=fwd:grad with 0 = m-fastest, 1 = n-fastest (e.g. "1:0")
+int tile_order(bool grad, int dflt) {
+  static int v[2] = {-1, -1};
+  if (v[0] < 0) {
+    v[0] = v[1] = -2;
+    const char* e = getenv("JSD_TILE_ORDER");
+    if (e && strlen(e) >= 3) {
+      v[0] = e[0] - '0';
+      v[1] = e[2] - '0';
+    }
+  }
+  const int x = v[grad ? 1 : 0];
+  return (x == 0 || x == 1) ? x : dflt;
+}
+
 int pick_cta_group(int64_t m_rows) {
   static int forced = -1;
   if (forced < 0) {
@@ -293,7 +308,7 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   p.M = (int)M;
   p.N = (int)N;
   p.K = (int)D;
-  p.n_fastest = 0;
+  p.n_fastest = tile_order(false, 0);
   p.row_offset = (int)row_offset;
   p.t_dev = t_dev;
   p.gmat = (__nv_bfloat16*)Gmat;
@@ -344,7 +359,7 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
   p.M = (int)rows;
   p.N = (int)D;
   p.K = (int)kdim;
-  p.n_fastest = 1;
+  p.n_fastest = tile_order(true, 1);
   p.t_dev = t_dev;
   p.gamma_dev = gamma_dev;
   p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;

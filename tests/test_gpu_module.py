@@ -276,3 +276,19 @@ def test_stress_slab_65536_columns():
     assert relerr(df, ref_df) < GRAD_RTOL
     assert float((f * df).sum(-1).abs().max()) < 1e-3 * float(df.abs().max() * f.norm(dim=-1).max())
     assert torch.isfinite(dt)
+
+
+def test_graphed_gathered_step_single_process_matches_eager(ops):
+    """The segmented CUDA-graph step of the data-parallel path (world size 1 here) equals the eager autograd path."""
+    from clip_lite_b200 import parallel
+    f, g = orc.synth_embeddings(512, 128, seed=9, correlated=True)
+    f, g = f.cuda(), g.cuda()
+    t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
+    gs = parallel.GraphedGatheredStep(f, g, t)
+    for seed in (9, 10):
+        f2, g2 = orc.synth_embeddings(512, 128, seed=seed, correlated=True)
+        loss, df, dg, dt = gs(f2.cuda(), g2.cuda())
+        fl, gl = f2.cuda().requires_grad_(True), g2.cuda().requires_grad_(True)
+        ref_loss, _ = parallel.gathered_dense_loss(fl, gl, t)
+        rdf, rdg, rdt = torch.autograd.grad(ref_loss, (fl, gl, t))
+        assert torch.equal(loss, ref_loss) and torch.equal(df, rdf) and torch.equal(dg, rdg) and torch.equal(dt, rdt)

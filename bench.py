@@ -212,7 +212,26 @@ def run_b200(args, wl):
     t_dev = torch.tensor(T_INIT, device=dev, requires_grad=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    # N > 1: the two exchange steps either fused into the kernels over NVLink peer memory (default) or as NCCL
+    # collectives (--exchange nccl); a peer set-up failure (no CUDA IPC on the box) is reported and NCCL used
+    exchange = "none"
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "peer":
+            try:
+                from clip_lite_b200 import peer
+                peer.get_exchange(rows, dim)
+            except Exception as exc:
+                print(f"[bench] peer exchange unavailable ({type(exc).__name__}: {exc}); NCCL collectives",
+                      file=sys.stderr)
+                exchange = "nccl"
+            ok = torch.tensor(1 if exchange == "peer" else 0, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            exchange = "peer" if int(ok) == 1 else "nccl"
+
     def loss_fn(f, g):
+        if exchange == "peer":
+            return peer.peer_dense_loss(f, g, t_dev)[0]
         if world > 1:
             return parallel.gathered_dense_loss(f, g, t_dev)[0]
         return ops.jsd_dense_loss(f, g, t_dev)[0]
@@ -229,6 +248,8 @@ def run_b200(args, wl):
             if world == 1:
                 from clip_lite_b200.graph import GraphedStep
                 gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
+            elif exchange == "peer":   # no collective call in the step: one graph launch per step
+                gs = peer.PeerGraphedStep(f_dev, g_dev, t_dev)
             else:      # NCCL is not captured: graph segments between the two eagerly launched collectives
                 gs = parallel.GraphedGatheredStep(f_dev, g_dev, t_dev)
             step, graphed = gs, True
@@ -372,14 +393,16 @@ def run_b200(args, wl):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = time_cpu(batch, dim, budget_s=20.0)
-        launches_per_step = 8                          # normalize x2, fwd + finalize, dU, dV, normalize_bwd x2
+        # library launches per step -- 1 GPU: normalise pair, fwd (+ loss), dU, dV, both Jacobians (+ dL/dt);
+        # N GPUs: normalise(+push), fwd, dU, image Jacobian, dV(+push), text Jacobian
+        launches_per_step = 5 if world == 1 else 6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "rows_per_gpu": rows,
-                       "neg_mode": "dense", "parallelism": f"dp{world}", "cuda_graph": graphed,
+                       "neg_mode": "dense", "parallelism": f"dp{world}", "cuda_graph": graphed, "exchange": exchange,
                        "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
                        "inputs": "bf16 unit rows resident in HBM; N(0,1) features, text = 0.6 img + 0.8 noise"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
@@ -402,6 +425,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="dense_b8192_d1024")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the step as one CUDA graph (default 1)")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: exchange fused into the kernels over NVLink peer memory, or NCCL collectives")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -32,13 +32,12 @@ SIGNATURES = {
                                   c_void_p]),
     "jsd_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "jsd_sum_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_cast_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "jsd_dense_backward_image_side": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                               c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                              c_void_p, c_void_p, c_void_p, c_void_p]),
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_streamk_workspace_bytes": (c_size_t, []),
     "jsd_streamk_flag_bytes": (c_size_t, []),
     "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
@@ -46,12 +45,37 @@ SIGNATURES = {
     "jsd_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_bwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
-                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "jsd_peer_flag_bytes": (c_size_t, []),
+    "jsd_peer_alloc": (c_int, [c_size_t, c_void_p]),
+    "jsd_peer_free": (c_int, [c_void_p]),
+    "jsd_peer_export": (c_int, [c_void_p, c_void_p]),
+    "jsd_peer_open": (c_int, [c_void_p, c_void_p]),
+    "jsd_peer_close": (c_int, [c_void_p]),
+    "jsd_peer_normalize_push": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    "jsd_peer_dense_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
+    "jsd_peer_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_peer_normalize_bwd_text": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p]),
     "jsd_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64,
                               c_void_p, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 5
+MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
+
+
+class PeerCtx(ctypes.Structure):
+    """struct jsd_peer_ctx of include/jsd_b200.h."""
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("rows", c_int64), ("dim", c_int64),
+                ("v_all", (c_void_p * MAX_PEERS) * 2), ("stage", c_void_p * MAX_PEERS),
+                ("flags", c_void_p * MAX_PEERS)]
+
+
+ABI_VERSION = 6
 _lib = None
 
 

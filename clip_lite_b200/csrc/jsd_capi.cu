@@ -194,43 +194,43 @@ int launch_index(const void* F, const void* G, int64_t B, int64_t D, const int32
 }
 
 template <typename T>
-int launch_normalize(const void* X, int64_t rows, int64_t D, void* Xn, float* inv_norm, cudaStream_t st) {
-  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xn)) & 15) == 0;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+int launch_normalize(const jsd::NormalizeJob& job, int count, int64_t rows, int64_t D, cudaStream_t st) {
+  uintptr_t bits = 0;
+  for (int i = 0; i < count; ++i) bits |= reinterpret_cast<uintptr_t>(job.X[i]) | reinterpret_cast<uintptr_t>(job.Xn[i]);
+  const bool vec = (D % 4 == 0) && (bits & 15) == 0;
+  const dim3 grid((unsigned)((rows + 7) / 8), (unsigned)count);
   if (vec && D % 128 == 0 && D / 128 <= jsd::ROW_REG_CHUNKS)
-    jsd::normalize_cast_reg_kernel<T><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)(D / 128),
-                                                            (__nv_bfloat16*)Xn, inv_norm);
+    jsd::normalize_cast_reg_kernel<T><<<grid, 256, 0, st>>>(job, (int)rows, (int)(D / 128));
   else if (vec)
-    jsd::normalize_cast_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, (__nv_bfloat16*)Xn, inv_norm);
+    jsd::normalize_cast_kernel<T, 4><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);
   else
-    jsd::normalize_cast_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, (__nv_bfloat16*)Xn, inv_norm);
+    jsd::normalize_cast_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <typename T>
-int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
-                         const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
-                         const float* gamma_dev, float inv_rows, void* dX, float* rowdot, cudaStream_t st) {
-  const bool vec = (D % 4 == 0) &&
-                   ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(dX) | reinterpret_cast<uintptr_t>(acc) |
-                     reinterpret_cast<uintptr_t>(partner)) & 15) == 0;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+int launch_normalize_bwd(const jsd::NormBwdJob& job, int count, int64_t rows, int64_t D, const float* gdiag,
+                         const float* t_dev, const float* gamma_dev, float inv_rows, cudaStream_t st) {
+  uintptr_t bits = 0;
+  for (int i = 0; i < count; ++i)
+    bits |= reinterpret_cast<uintptr_t>(job.X[i]) | reinterpret_cast<uintptr_t>(job.dX[i]) |
+            reinterpret_cast<uintptr_t>(job.acc[i]) | reinterpret_cast<uintptr_t>(job.partner[i]);
+  const bool vec = (D % 4 == 0) && (bits & 15) == 0;
+  const dim3 grid((unsigned)((rows + 7) / 8), (unsigned)count);
   if (vec && D % 128 == 0 && D / 128 <= jsd::ROW_REG_CHUNKS)
-    jsd::normalize_bwd_reg_kernel<T><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)(D / 128), inv_norm, acc,
-                                                           (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
-                                                           gamma_dev, inv_rows, (T*)dX, rowdot);
+    jsd::normalize_bwd_reg_kernel<T><<<grid, 256, 0, st>>>(job, (int)rows, (int)(D / 128), gdiag, t_dev, gamma_dev,
+                                                           inv_rows);
   else if (vec)
-    jsd::normalize_bwd_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
-                                                        (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
-                                                        gamma_dev, inv_rows, (T*)dX, rowdot);
+    jsd::normalize_bwd_kernel<T, 4><<<grid, 256, 0, st>>>(job, (int)rows, (int)D, gdiag, t_dev, gamma_dev, inv_rows);
   else
-    jsd::normalize_bwd_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)X, (int)rows, (int)D, inv_norm, acc,
-                                                        (const __nv_bfloat16*)partner, partner_offset, gdiag, t_dev,
-                                                        gamma_dev, inv_rows, (T*)dX, rowdot);
+    jsd::normalize_bwd_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D, gdiag, t_dev, gamma_dev, inv_rows);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// the second int of the forward workspace's 16-byte ticket area serialises the dL/dt reduction
+int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; }
 
 #define JSD_DISPATCH_DTYPE(dtype, CALL)                                    \
   switch (dtype) {                                                         \
@@ -244,7 +244,7 @@ int launch_normalize_bwd(const void* X, int64_t rows, int64_t D, const float* in
 
 extern "C" {
 
-int jsd_abi_version(void) { return 5; }
+int jsd_abi_version(void) { return 6; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -279,17 +279,62 @@ int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* 
   JSD_REQUIRE(X && Xn && inv_norm, "jsd_normalize_cast: null pointer argument");
   JSD_REQUIRE(fits_int(rows) && fits_int(D), "jsd_normalize_cast: rows=%lld, D=%lld out of range", (long long)rows,
               (long long)D);
+  jsd::NormalizeJob job{};
+  job.X[0] = X;
+  job.Xn[0] = (__nv_bfloat16*)Xn;
+  job.inv_norm[0] = inv_norm;
   cudaStream_t st = (cudaStream_t)stream;
-  JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(X, rows, D, Xn, inv_norm, st)));
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(job, 1, rows, D, st)));
+}
+
+int jsd_normalize_cast_pair(const void* F, const void* G, int dtype, int64_t rows, int64_t D, void* U, void* V,
+                            float* inv_f, float* inv_g, jsd_stream_t stream) {
+  JSD_REQUIRE(F && G && U && V && inv_f && inv_g, "jsd_normalize_cast_pair: null pointer argument");
+  JSD_REQUIRE(fits_int(rows) && fits_int(D), "jsd_normalize_cast_pair: rows=%lld, D=%lld out of range",
+              (long long)rows, (long long)D);
+  jsd::NormalizeJob job{};
+  job.X[0] = F;
+  job.X[1] = G;
+  job.Xn[0] = (__nv_bfloat16*)U;
+  job.Xn[1] = (__nv_bfloat16*)V;
+  job.inv_norm[0] = inv_f;
+  job.inv_norm[1] = inv_g;
+  cudaStream_t st = (cudaStream_t)stream;
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(job, 2, rows, D, st)));
 }
 
 size_t jsd_dense_workspace_bytes(void) {
-  return (size_t)1024 * jsd::NUM_EPI_WARPS * jsd::PARTIALS_PER_WARP * sizeof(float);   // up to 1024 CTAs
+  return 16 + (size_t)1024 * jsd::NUM_EPI_WARPS * jsd::PARTIALS_PER_WARP * sizeof(float);   // ticket + up to 1024 CTAs
 }
+
+}  // extern "C"
+
+namespace {
+struct PeerWait {
+  const int* flags = nullptr;
+  const int* counter = nullptr;
+  int count = 0;
+};
+int dense_fwd_impl(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
+                   const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
+                   float* loss_out, const PeerWait& wait, jsd_stream_t stream);
+}  // namespace
+
+extern "C" {
 
 int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                   const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
                   float* loss_out, jsd_stream_t stream) {
+  return dense_fwd_impl(U, V, M, N, D, row_offset, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, PeerWait{},
+                        stream);
+}
+
+}  // extern "C"
+
+namespace {
+int dense_fwd_impl(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
+                   const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
+                   float* loss_out, const PeerWait& wait, jsd_stream_t stream) {
   JSD_REQUIRE(U && V && t_dev && gdiag && workspace && out4, "jsd_dense_fwd: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_fwd: M=%lld N=%lld D=%lld out of range",
               (long long)M, (long long)N, (long long)D);
@@ -314,23 +359,27 @@ int jsd_dense_fwd(const void* U, const void* V, int64_t M, int64_t N, int64_t D,
   p.gmat = (__nv_bfloat16*)Gmat;
   p.ldg = ldg;
   p.gdiag = gdiag;
-  p.partials = (float*)workspace;
+  // workspace = [ticket (16 bytes, zero between launches) | per-warp partial sums]
+  p.ticket = (int*)workspace;
+  p.partials = (float*)((char*)workspace + 16);
+  p.out4 = out4;
+  p.loss_out = loss_out;
+  p.inv_pos = 1.0 / (double)M;
+  p.inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
+  p.wait_flags = wait.flags;
+  p.wait_counter = wait.counter;
+  p.wait_count = wait.count;
   if (Gmat) {
     // epilogue TMA stores: box = 64 columns x 32 rows per warp; rows >= M / columns >= N are clipped
     if (int rc = make_tmap(&p.tmG, Gmat, N, M, ldg, jsd::COLS_PER_WARP, 32)) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = 0;
-  if (int rc = cg == 2 ? launch_gemm<jsd::MODE_FWD, false, false, 2>(tmA, tmB, p, nullptr, st, &grid)
-                       : launch_gemm<jsd::MODE_FWD, false, false, 1>(tmA, tmB, p, nullptr, st, &grid))
-    return rc;
-  const double inv_pos = 1.0 / (double)M;
-  const double inv_neg = N > 1 ? 1.0 / ((double)M * (double)(N - 1)) : 0.0;
-  jsd::finalize_dense_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>((const float*)workspace, grid * jsd::NUM_EPI_WARPS, inv_pos, inv_neg,
-                                                t_dev, out4, loss_out);
-  JSD_CUDA_OK(cudaGetLastError());
-  return 0;
+  return cg == 2 ? launch_gemm<jsd::MODE_FWD, false, false, 2>(tmA, tmB, p, nullptr, st)
+                 : launch_gemm<jsd::MODE_FWD, false, false, 1>(tmA, tmB, p, nullptr, st);
 }
+}  // namespace
+
+extern "C" {
 
 size_t jsd_streamk_flag_bytes(void) { return streamk_flag_bytes(); }
 
@@ -340,8 +389,8 @@ size_t jsd_streamk_workspace_bytes(void) {
 
 static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* X, int64_t M, int64_t N, int64_t D,
                             const float* t_dev, const float* gamma_dev, void* sk_workspace, float* out,
-                            jsd_stream_t stream) {
-  JSD_REQUIRE(Gmat && X && t_dev && out, "jsd_dense_bwd: null pointer argument");
+                            jsd_stream_t stream, const jsd_peer_ctx* peer = nullptr) {
+  JSD_REQUIRE(Gmat && X && t_dev && (out || peer), "jsd_dense_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_bwd: M=%lld N=%lld D=%lld out of range",
               (long long)M, (long long)N, (long long)D);
   JSD_REQUIRE(D % 8 == 0, "jsd_dense_bwd: D must be a multiple of 8");
@@ -365,6 +414,19 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
   p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;
   p.out = out;
   p.ldo = D;
+  if (peer != nullptr) {
+    // rows of dV_all are global text rows: row j belongs to rank j / rows_per_rank, which receives this rank's
+    // fp32 partial in slot `rank` of its staging buffer
+    p.peer_rows = (int)peer->rows;
+    p.peer_world = peer->world;
+    int32_t* mine = peer->flags[peer->rank];
+    for (int q = 0; q < peer->world; ++q) {
+      p.peer_out[q] = (float*)peer->stage[q] + (size_t)peer->rank * peer->rows * D;
+      p.peer_flag_dst[q] = peer->flags[q] + JSD_PEER_READY_DV + peer->rank;
+    }
+    p.peer_counter = mine + JSD_PEER_COUNTER_DV;
+    p.peer_ticket = mine + JSD_PEER_TICKET_DV;
+  }
   return launch_gemm_any<jsd::MODE_GRAD>(dv, true, pick_cta_group(rows), tmA, tmB, p, sk_workspace,
                                           (cudaStream_t)stream);
 }
@@ -383,60 +445,202 @@ int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, int64_t M, in
 
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
-                      const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, jsd_stream_t stream) {
+                      const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, void* workspace, float* dt_out,
+                      jsd_stream_t stream) {
   JSD_REQUIRE(X && inv_norm && acc && partner && t_dev && dX, "jsd_normalize_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(rows) && fits_int(D) && M_rows > 0, "jsd_normalize_bwd: bad shape");
+  JSD_REQUIRE(dt_out == nullptr || (rowdot && workspace), "jsd_normalize_bwd: dt_out needs rowdot and the workspace");
+  jsd::NormBwdJob job{};
+  job.X[0] = X;
+  job.inv_norm[0] = inv_norm;
+  job.acc[0] = acc;
+  job.partner[0] = (const __nv_bfloat16*)partner;
+  job.partner_offset[0] = partner_offset;
+  job.dX[0] = dX;
+  job.rowdot = rowdot;
+  job.ticket = dt_out ? dt_ticket(workspace) : nullptr;
+  job.dt_out = dt_out;
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_rows = (float)(1.0 / (double)M_rows);
-  JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(X, rows, D, inv_norm, acc, partner, partner_offset, gdiag, t_dev,
-                                                     gamma_dev, inv_rows, dX, rowdot, st)));
-}
-
-int jsd_sum_f32(const float* x, int64_t n, float* out, jsd_stream_t stream) {
-  JSD_REQUIRE(x && out && fits_int(n), "jsd_sum_f32: bad argument");
-  jsd::sum_kernel<<<1, jsd::FINALIZE_THREADS, 0, (cudaStream_t)stream>>>(x, (int)n, out);
-  JSD_CUDA_OK(cudaGetLastError());
-  return 0;
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 1, rows, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
 }
 
 int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U,
                       void* V, float* inv_f, float* inv_g, void* Gmat, int64_t ldg, float* gdiag, void* workspace,
                       float* out4, float* loss_out, jsd_stream_t stream) {
-  if (int rc = jsd_normalize_cast(F, dtype, B, D, U, inv_f, stream)) return rc;
-  if (int rc = jsd_normalize_cast(G, dtype, B, D, V, inv_g, stream)) return rc;
+  if (int rc = jsd_normalize_cast_pair(F, G, dtype, B, D, U, V, inv_f, inv_g, stream)) return rc;
   return jsd_dense_fwd(U, V, B, B, D, 0, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, stream);
 }
 
 int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U, const void* V,
                        const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg, const float* gdiag,
                        const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v, float* rowdot,
-                       void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
-  JSD_REQUIRE(dt_out && acc_u && acc_v && rowdot, "jsd_dense_backward: null pointer argument");
+                       void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
+  JSD_REQUIRE(F && G && U && V && inv_f && inv_g && gdiag && dF && dG, "jsd_dense_backward: null pointer argument");
+  JSD_REQUIRE(dt_out && acc_u && acc_v && rowdot && workspace, "jsd_dense_backward: null pointer argument");
   if (int rc = jsd_dense_bwd_du(Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
   if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
-  if (int rc = jsd_normalize_bwd(F, dtype, B, D, inv_f, acc_u, V, 0, gdiag, t_dev, gamma_dev, B, dF, rowdot, stream))
-    return rc;
-  if (int rc = jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, stream))
-    return rc;
-  return jsd_sum_f32(rowdot, B, dt_out, stream);     // gamma * dL/dt = sum_i <u_i, dU_i>
-}
-
-int jsd_normalize_cast_pair(const void* F, const void* G, int dtype, int64_t rows, int64_t D, void* U, void* V,
-                            float* inv_f, float* inv_g, jsd_stream_t stream) {
-  if (int rc = jsd_normalize_cast(F, dtype, rows, D, U, inv_f, stream)) return rc;
-  return jsd_normalize_cast(G, dtype, rows, D, V, inv_g, stream);
+  // both Jacobians (image side = job 0, text side = job 1) and gamma * dL/dt = sum_i <u_i, dU_i> in one launch
+  jsd::NormBwdJob job{};
+  job.X[0] = F;
+  job.X[1] = G;
+  job.inv_norm[0] = inv_f;
+  job.inv_norm[1] = inv_g;
+  job.acc[0] = acc_u;
+  job.acc[1] = acc_v;
+  job.partner[0] = (const __nv_bfloat16*)V;
+  job.partner[1] = (const __nv_bfloat16*)U;
+  job.dX[0] = dF;
+  job.dX[1] = dG;
+  job.rowdot = rowdot;
+  job.ticket = dt_ticket(workspace);
+  job.dt_out = dt_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_rows = (float)(1.0 / (double)B);
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 2, B, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
 }
 
 int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                                   const void* V_all, const float* inv_f, const void* Gmat, int64_t ldg,
                                   const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                                  float* rowdot, void* dF, float* dt_out, jsd_stream_t stream) {
-  JSD_REQUIRE(acc_u && rowdot && dt_out, "jsd_dense_backward_image_side: null pointer argument");
+                                  float* rowdot, void* workspace, void* dF, float* dt_out, jsd_stream_t stream) {
+  JSD_REQUIRE(acc_u && rowdot && dt_out && workspace, "jsd_dense_backward_image_side: null pointer argument");
   if (int rc = jsd_dense_bwd_du(Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
-  if (int rc = jsd_normalize_bwd(F, dtype, M, D, inv_f, acc_u, V_all, row_offset, gdiag, t_dev, gamma_dev, M, dF,
-                                 rowdot, stream))
-    return rc;
-  return jsd_sum_f32(rowdot, M, dt_out, stream);
+  return jsd_normalize_bwd(F, dtype, M, D, inv_f, acc_u, V_all, row_offset, gdiag, t_dev, gamma_dev, M, dF, rowdot,
+                           workspace, dt_out, stream);
+}
+
+/* ------------------------------------------------------------------ peer-memory exchange */
+static int check_peer_ctx(const jsd_peer_ctx* c, const char* who) {
+  JSD_REQUIRE(c != nullptr, "%s: null context", who);
+  JSD_REQUIRE(c->world >= 1 && c->world <= JSD_MAX_PEERS && c->rank >= 0 && c->rank < c->world,
+              "%s: bad rank %d / world %d", who, c->rank, c->world);
+  JSD_REQUIRE(fits_int(c->rows) && fits_int(c->dim) && fits_int(c->rows * c->world), "%s: bad shape", who);
+  for (int q = 0; q < c->world; ++q)
+    JSD_REQUIRE(c->v_all[0][q] && c->v_all[1][q] && c->stage[q] && c->flags[q], "%s: null buffer of rank %d", who, q);
+  return 0;
+}
+
+size_t jsd_peer_flag_bytes(void) { return JSD_PEER_FLAG_INTS * sizeof(int32_t); }
+
+int jsd_peer_alloc(size_t bytes, void** out) {
+  JSD_REQUIRE(out && bytes > 0, "jsd_peer_alloc: bad argument");
+  JSD_CUDA_OK(cudaMalloc(out, bytes));
+  JSD_CUDA_OK(cudaMemset(*out, 0, bytes));
+  JSD_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int jsd_peer_free(void* ptr) {
+  JSD_CUDA_OK(cudaFree(ptr));
+  return 0;
+}
+
+int jsd_peer_export(void* ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == JSD_PEER_HANDLE_BYTES, "IPC handle size");
+  JSD_REQUIRE(ptr && handle64, "jsd_peer_export: null pointer argument");
+  cudaIpcMemHandle_t h;
+  JSD_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+
+int jsd_peer_open(const void* handle64, void** out) {
+  JSD_REQUIRE(handle64 && out, "jsd_peer_open: null pointer argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  JSD_CUDA_OK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int jsd_peer_close(void* ptr) {
+  JSD_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity, void* U,
+                            float* inv_f, float* inv_g, jsd_stream_t stream) {
+  if (int rc = check_peer_ctx(ctx, "jsd_peer_normalize_push")) return rc;
+  JSD_REQUIRE(F && G && U && inv_f && inv_g && (parity == 0 || parity == 1), "jsd_peer_normalize_push: bad argument");
+  const int64_t rows = ctx->rows, D = ctx->dim;
+  jsd::PeerPushJob job{};
+  job.X[0] = F;
+  job.X[1] = G;
+  job.U = (__nv_bfloat16*)U;
+  job.inv_norm[0] = inv_f;
+  job.inv_norm[1] = inv_g;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(U);
+  for (int q = 0; q < ctx->world; ++q) {
+    job.v_dst[q] = (__nv_bfloat16*)ctx->v_all[parity][q] + (size_t)ctx->rank * rows * D;
+    job.flag_dst[q] = ctx->flags[q] + JSD_PEER_READY_V + parity * JSD_MAX_PEERS + ctx->rank;
+    bits |= reinterpret_cast<uintptr_t>(job.v_dst[q]);
+  }
+  int32_t* mine = ctx->flags[ctx->rank];
+  job.counter = mine + JSD_PEER_COUNTER_V + parity;
+  job.ticket = mine + JSD_PEER_TICKET_PUSH;
+  job.world = ctx->world;
+  const bool vec = (D % 4 == 0) && (bits & 15) == 0;
+  const dim3 grid((unsigned)((rows + 7) / 8), 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+#define JSD_PUSH_CASE(code, T)                                                                        \
+    case code:                                                                                        \
+      if (vec) jsd::normalize_push_kernel<T, 4><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);        \
+      else jsd::normalize_push_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);            \
+      break;
+    JSD_PUSH_CASE(JSD_F32, float)
+    JSD_PUSH_CASE(JSD_BF16, __nv_bfloat16)
+    JSD_PUSH_CASE(JSD_F16, __half)
+#undef JSD_PUSH_CASE
+    default: return fail("unsupported dtype code %d", dtype);
+  }
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int jsd_peer_dense_fwd(const void* U, const jsd_peer_ctx* ctx, int parity, const float* t_dev, void* Gmat,
+                       int64_t ldg, float* gdiag, void* workspace, float* out4, float* loss_out,
+                       jsd_stream_t stream) {
+  if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_fwd")) return rc;
+  JSD_REQUIRE(parity == 0 || parity == 1, "jsd_peer_dense_fwd: parity must be 0 or 1");
+  const int32_t* mine = ctx->flags[ctx->rank];
+  PeerWait w;
+  w.flags = mine + JSD_PEER_READY_V + parity * JSD_MAX_PEERS;
+  w.counter = mine + JSD_PEER_COUNTER_V + parity;
+  w.count = ctx->world;
+  return dense_fwd_impl(U, ctx->v_all[parity][ctx->rank], ctx->rows, ctx->rows * ctx->world, ctx->dim,
+                        ctx->rows * ctx->rank, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, w, stream);
+}
+
+int jsd_peer_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
+                          const float* gamma_dev, jsd_stream_t stream) {
+  if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_bwd_dv")) return rc;
+  return dense_bwd_common(true, Gmat, ldg, U, ctx->rows, ctx->rows * ctx->world, ctx->dim, t_dev, gamma_dev, nullptr,
+                          nullptr, stream, ctx);
+}
+
+int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g, const void* U,
+                                const float* gdiag, const float* t_dev, const float* gamma_dev, void* dG,
+                                jsd_stream_t stream) {
+  if (int rc = check_peer_ctx(ctx, "jsd_peer_normalize_bwd_text")) return rc;
+  JSD_REQUIRE(G && inv_g && U && gdiag && t_dev && dG, "jsd_peer_normalize_bwd_text: null pointer argument");
+  const int32_t* mine = ctx->flags[ctx->rank];
+  jsd::NormBwdJob job{};
+  job.X[0] = G;
+  job.inv_norm[0] = inv_g;
+  job.acc[0] = (const float*)ctx->stage[ctx->rank];
+  job.partner[0] = (const __nv_bfloat16*)U;
+  job.partner_offset[0] = 0;
+  job.dX[0] = dG;
+  job.acc_slots = ctx->world;
+  job.acc_slot_stride = (long long)ctx->rows * ctx->dim;
+  job.wait_flags = mine + JSD_PEER_READY_DV;
+  job.wait_counter = mine + JSD_PEER_COUNTER_DV;
+  job.wait_count = ctx->world;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_rows = (float)(1.0 / (double)ctx->rows);
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 1, ctx->rows, ctx->dim, gdiag, t_dev, gamma_dev, inv_rows,
+                                                     st)));
 }
 
 int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,

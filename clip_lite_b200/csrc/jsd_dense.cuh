@@ -55,6 +55,7 @@ constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;       // 512
 constexpr int PARTIALS_PER_WARP = 4;                  // sum sp(-x_pos), sum max(s,0), sum log2(1+e), spare
 constexpr int SK_SLOT_FLOATS = BLOCK_M * BLOCK_N;     // one fp32 partial accumulator tile (per CTA)
 constexpr int SK_MAX_CTAS = 256;                      // flags / slots reserved in the workspace
+constexpr int MAX_PEERS = 8;                          // GPUs of one NVSwitch domain
 
 // per-CTA shared-memory budget as a function of the CTA-group size (1 = single CTA, 2 = CTA pair)
 __host__ __device__ constexpr int b_rows_per_cta(int cg) { return BLOCK_N / cg; }
@@ -92,6 +93,10 @@ struct GemmParams {
   long long ldg;
   float* gdiag;          // [M]
   float* partials;       // [grid * NUM_EPI_WARPS * PARTIALS_PER_WARP]
+  int* ticket;           // zero before the launch; the last CTA to finish reduces the partials and re-zeroes it
+  float* out4;           // {pos, neg, pos + neg, 0}
+  float* loss_out;       // optional separate copy of the loss
+  double inv_pos, inv_neg;   // 1 / M,  1 / (M (N - 1))
   // GRAD
   const float* gamma_dev;  // may be null (gamma = 1)
   float scale;             // 1 / (M_rows * (N_cols - 1))
@@ -102,6 +107,19 @@ struct GemmParams {
   int stream_k;
   int* sk_flags;
   float* sk_slots;
+  // peer-memory exchange (multi-GPU, see jsd_peer.cuh).  wait_*: the TMA producer holds its first load until every
+  // rank's flag has reached *wait_counter (the gathered B operand was written by peer GPUs).  peer_*: GRAD
+  // epilogue stores row r of the output into rank (r / peer_rows)'s buffer (peer_out[q], row r % peer_rows); the
+  // last CTA of the launch then bumps *peer_counter and publishes it to every rank's flag (system scope).
+  const int* wait_flags;
+  const int* wait_counter;
+  int wait_count;
+  int peer_rows;                 // 0 = plain local output
+  int peer_world;
+  float* peer_out[MAX_PEERS];
+  int* peer_flag_dst[MAX_PEERS];
+  int* peer_counter;
+  int* peer_ticket;
 };
 
 // Score of a masked (out-of-range) pair: tau * kMaskedScore is finite and so negative that
@@ -271,6 +289,11 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (CG == 2) tma_load_2d_pair(dst, m, full0 + 8u * s, c0, c1);
         else tma_load_2d(dst, m, full0 + 8u * s, c0, c1);
       };
+      if (p.wait_flags != nullptr) {
+        // the B operand was gathered by peer GPUs writing into this GPU's memory: wait for their "rows are in" flags
+        wait_flags_sys(p.wait_flags, p.wait_count, *p.wait_counter);
+        fence_proxy_async_all();
+      }
       SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
@@ -514,7 +537,13 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (row_ok) {
-            float* dst = p.out + (long long)grow * p.ldo + col0;
+            float* dst;
+            if (p.peer_rows > 0) {           // the row's owner rank receives this rank's partial (NVLink store)
+              const int owner = grow / p.peer_rows;
+              dst = p.peer_out[owner] + (long long)(grow - owner * p.peer_rows) * p.ldo + col0;
+            } else {
+              dst = p.out + (long long)grow * p.ldo + col0;
+            }
             if (col0 + CW <= p.N) {
 #pragma unroll
               for (int k4 = 0; k4 < CW / 4; ++k4) {
@@ -590,6 +619,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         acc_phase ^= 1u;
       }
     }
+    if constexpr (MODE == MODE_GRAD) {
+      if (p.peer_rows > 0) __threadfence_system();   // this thread's peer stores, before the CTA takes its ticket
+    }
     if constexpr (MODE == MODE_FWD) {
       if (p.gmat != nullptr && lane == 0) tma_store_wait_all();   // smem must outlive the last store
       pos_sum = warp_sum(pos_sum);
@@ -601,6 +633,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         dst[1] = relu_sum;
         dst[2] = lg_sum;
         dst[3] = 0.f;
+        __threadfence();   // visible device-wide before this CTA takes its finalisation ticket
       }
     }
   }
@@ -611,6 +644,70 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+
+  if constexpr (MODE == MODE_GRAD) {
+    // Peer exchange: once every CTA's stores are fenced, the last CTA publishes "this rank's partials are in".
+    if (p.peer_rows > 0) {
+      int* s_last = reinterpret_cast<int*>(smem_raw);
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        *s_last = (atomicAdd(p.peer_ticket, 1) == (int)gridDim.x - 1);
+      }
+      __syncthreads();
+      if (*s_last && threadIdx.x == 0) {
+        __threadfence_system();
+        const int e = *p.peer_counter + 1;
+        *p.peer_counter = e;
+        for (int q = 0; q < p.peer_world; ++q) st_release_sys(p.peer_flag_dst[q], e);
+        *p.peer_ticket = 0;
+      }
+    }
+  }
+
+  if constexpr (MODE == MODE_FWD) {
+    // Loss finalisation without a second launch: the last CTA to get here reduces every warp's partial sums
+    // in a fixed order (fp64, deterministic).  The pipeline is drained, so the operand ring is free scratch.
+    //   pos = P0 / M,   neg = (tau * P1 + ln2 * P2) / (M (N - 1))
+    int* s_last = reinterpret_cast<int*>(smem_raw);
+    double* sh = reinterpret_cast<double*>(smem_raw + 16);
+    if (threadIdx.x == 0) {
+      __threadfence();                                  // this CTA's partials (written before the barrier above)
+      *s_last = (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      const int n = (int)gridDim.x * NUM_EPI_WARPS;
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int i = threadIdx.x; i < n; i += GEMM_THREADS)
+        for (int k = 0; k < 3; ++k) acc[k] += (double)__ldcg(p.partials + (size_t)i * PARTIALS_PER_WARP + k);
+      // fixed reduction tree (warp butterflies, then the 20 warp totals in order): short dependent fp64 chains
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+        if (lane == 0) sh[k * 32 + warp] = acc[k];
+      }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        double tot = 0.0;
+        for (int w = 0; w < GEMM_THREADS / 32; ++w) tot += sh[threadIdx.x * 32 + w];
+        sh[96 + threadIdx.x] = tot;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const double tau = exp((double)*p.t_dev);
+        const double pos = sh[96] * p.inv_pos;
+        const double neg = (tau * sh[97] + 0.6931471805599453 * sh[98]) * p.inv_neg;
+        p.out4[0] = (float)pos;
+        p.out4[1] = (float)neg;
+        p.out4[2] = (float)(pos + neg);
+        p.out4[3] = 0.f;
+        if (p.loss_out) *p.loss_out = (float)(pos + neg);
+        *p.ticket = 0;                                  // re-armed for the next launch on this stream
+      }
+    }
   }
 }
 

@@ -306,10 +306,19 @@ finalize_kernel(const float* __restrict__ partials, int n, int width, double inv
 
 // ------------------------------------------------------------------ normalise + cast (dense pre-pass)
 // One warp per row: Xn = bf16(x / max(||x||, eps)), inv_norm = 1 / max(||x||, eps).
+// One launch normalises up to two tensors of the same shape (blockIdx.y selects): F and G of a step.
+struct NormalizeJob {
+  const void* X[2];
+  __nv_bfloat16* Xn[2];
+  float* inv_norm[2];
+};
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-normalize_cast_kernel(const T* __restrict__ X, int rows, int D, __nv_bfloat16* __restrict__ Xn,
-                      float* __restrict__ inv_norm) {
+normalize_cast_kernel(const NormalizeJob job, int rows, int D) {
+  const T* __restrict__ X = static_cast<const T*>(job.X[blockIdx.y]);
+  __nv_bfloat16* __restrict__ Xn = job.Xn[blockIdx.y];
+  float* __restrict__ inv_norm = job.inv_norm[blockIdx.y];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -338,20 +347,162 @@ normalize_cast_kernel(const T* __restrict__ X, int rows, int D, __nv_bfloat16* _
   if (lane == 0) inv_norm[row] = inv;
 }
 
+// ------------------------------------------------------------------ normalise + cast + all-gather by peer stores
+// Multi-GPU forward pre-pass in ONE launch: blockIdx.y = 0 normalises the image rows into the local U;
+// blockIdx.y = 1 normalises the text rows and writes each bf16 unit row into EVERY rank's gathered V buffer
+// (plain stores to peer memory over NVLink: the all-gather is fused into the producer, there is no separate
+// collective and no second pass over the data).  The last block bumps this rank's counter and publishes it to
+// every rank's "rows of rank r are in" flag with system-scope release semantics.
+struct PeerPushJob {
+  const void* X[2];              // F rows, G rows [rows, D]
+  __nv_bfloat16* U;              // local image unit rows
+  float* inv_norm[2];
+  __nv_bfloat16* v_dst[8];       // rank q's gathered V buffer, already offset to this rank's first row
+  int* flag_dst[8];              // rank q's flag slot for this rank
+  int* counter;                  // local: pushes so far into this buffer
+  int* ticket;                   // local, zero between launches
+  int world;
+};
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_push_kernel(const PeerPushJob job, int rows, int D) {
+  const int jy = blockIdx.y;
+  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row < rows) {
+    const T* x = X + (size_t)row * D;
+    float ss = 0.f;
+    for_row<T, VEC>(D, lane, 32, [&](int d) {
+      if constexpr (VEC == 4) {
+        const float4 f = Vec4<T>::load(x + d);
+        ss += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+      } else {
+        const float f = to_f32(x[d]);
+        ss += f * f;
+      }
+    });
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), kNormEps);
+    const int ndst = jy == 0 ? 1 : job.world;
+    for_row<T, VEC>(D, lane, 32, [&](int d) {      // second read of the row comes from L1/L2
+      if constexpr (VEC == 4) {
+        const float4 f = Vec4<T>::load(x + d);
+        const float4 r = make_float4(f.x * inv, f.y * inv, f.z * inv, f.w * inv);
+        for (int q = 0; q < ndst; ++q)
+          Vec4<__nv_bfloat16>::store((jy == 0 ? job.U : job.v_dst[q]) + (size_t)row * D + d, r);
+      } else {
+        const __nv_bfloat16 r = __float2bfloat16_rn(to_f32(x[d]) * inv);
+        for (int q = 0; q < ndst; ++q) ((jy == 0 ? job.U : job.v_dst[q]) + (size_t)row * D)[d] = r;
+      }
+    });
+    if (lane == 0) job.inv_norm[jy][row] = inv;
+  }
+  __shared__ int s_last;
+  __threadfence_system();                            // this thread's peer stores
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(job.ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence_system();
+    const int e = *job.counter + 1;
+    *job.counter = e;
+    for (int q = 0; q < job.world; ++q) st_release_sys(job.flag_dst[q], e);
+    *job.ticket = 0;
+  }
+}
+
+// Last-block reduction of the row dots: dt_out = sum_i rowdot[i] (fp64, fixed order => deterministic).
+// Called by every thread of every block at the end of a normalise-backward kernel when dt_out != nullptr.
+__device__ __forceinline__ void reduce_rowdot_last_block(const float* rowdot, int rows, int* ticket, float* dt_out) {
+  __shared__ int s_last;
+  __shared__ double s_part[256];
+  __threadfence();                                   // this block's rowdot entries
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) acc += (double)__ldcg(rowdot + i);
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) s_part[threadIdx.x] += s_part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *dt_out = (float)s_part[0];
+    *ticket = 0;                                     // re-armed for the next launch on this stream
+  }
+}
+
 // ------------------------------------------------------------------ normalise backward (dense post-pass)
 // dU_row = acc_row + coef * gdiag[row] * partner[row + partner_offset]      (positive-pair term, fp32)
 // dX_row = (dU_row - u_row <u_row, dU_row>) * inv_norm[row],  u_row = x_row * inv_norm[row]
-// coef = gamma * tau / M_rows.  One warp per row.
+// coef = gamma * tau / M_rows.  One warp per row.  With dt_out != nullptr the last block also reduces the row
+// dots <u_i, dU_i> to gamma * dL/dt (no separate reduction launch).
+// One launch serves up to two row sets of the same shape (blockIdx.y selects): the image and the text side of
+// a single-GPU step.  Only job 0 (the image side) reports row dots / dL/dt.
+struct NormBwdJob {
+  const void* X[2];
+  const float* inv_norm[2];
+  const float* acc[2];
+  const __nv_bfloat16* partner[2];
+  long long partner_offset[2];
+  void* dX[2];
+  float* rowdot;     // job 0 only; may be null
+  int* ticket;       // zero between launches (needed iff dt_out != nullptr)
+  float* dt_out;     // may be null
+  // peer exchange (text side of a multi-GPU step): acc is `acc_slots` partial accumulators, `acc_slot_stride`
+  // floats apart, one per rank, summed here in rank order (deterministic); every block first waits until each
+  // rank's flag has reached *wait_counter ("my partial is in your buffer").
+  int acc_slots;               // <= 1: a single accumulator
+  long long acc_slot_stride;
+  const int* wait_flags;       // null: no wait
+  const int* wait_counter;
+  int wait_count;
+};
+
+__device__ __forceinline__ void normbwd_wait_peers(const NormBwdJob& job) {
+  if (job.wait_flags == nullptr) return;
+  if (threadIdx.x == 0) wait_flags_sys(job.wait_flags, job.wait_count, *job.wait_counter);
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 load_acc_slots(const float* a, int slots, long long stride) {
+  float4 g = __ldcg(reinterpret_cast<const float4*>(a));
+  for (int sl = 1; sl < slots; ++sl) {
+    const float4 h = __ldcg(reinterpret_cast<const float4*>(a + sl * stride));
+    g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+  }
+  return g;
+}
+__device__ __forceinline__ float load_acc_slots1(const float* a, int slots, long long stride) {
+  float g = __ldcg(a);
+  for (int sl = 1; sl < slots; ++sl) g += __ldcg(a + sl * stride);
+  return g;
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __restrict__ inv_norm,
-                     const float* __restrict__ acc, const __nv_bfloat16* __restrict__ partner,
-                     long long partner_offset, const float* __restrict__ gdiag, const float* __restrict__ t_dev,
-                     const float* __restrict__ gamma_dev, float inv_rows, T* __restrict__ dX,
-                     float* __restrict__ rowdot) {
+normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restrict__ gdiag,
+                     const float* __restrict__ t_dev, const float* __restrict__ gamma_dev, float inv_rows) {
+  const int jy = blockIdx.y;
+  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
+  const float* __restrict__ inv_norm = job.inv_norm[jy];
+  const float* __restrict__ acc = job.acc[jy];
+  const __nv_bfloat16* __restrict__ partner = job.partner[jy];
+  const long long partner_offset = job.partner_offset[jy];
+  T* __restrict__ dX = static_cast<T*>(job.dX[jy]);
+  float* __restrict__ rowdot = jy == 0 ? job.rowdot : nullptr;
+  const int slots = job.acc_slots;
+  const long long sstride = job.acc_slot_stride;
+  normbwd_wait_peers(job);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (row < rows) {
   const float gamma = gamma_dev ? *gamma_dev : 1.f;
   const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
   const float inv = inv_norm[row];
@@ -361,10 +512,10 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
   float dot = 0.f;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
-      const float4 f = Vec4<T>::load(x + d), g = Vec4<float>::load(a + d), q = Vec4<__nv_bfloat16>::load(pr + d);
+      const float4 f = Vec4<T>::load(x + d), g = load_acc_slots(a + d, slots, sstride), q = Vec4<__nv_bfloat16>::load(pr + d);
       dot += f.x * fmaf(c, q.x, g.x) + f.y * fmaf(c, q.y, g.y) + f.z * fmaf(c, q.z, g.z) + f.w * fmaf(c, q.w, g.w);
     } else {
-      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), a[d]);
+      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), load_acc_slots1(a + d, slots, sstride));
     }
   });
   dot = warp_sum(dot) * inv;   // <u, dU>
@@ -372,7 +523,7 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
   T* o = dX + (size_t)row * D;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
-      const float4 f = Vec4<T>::load(x + d), g = Vec4<float>::load(a + d), q = Vec4<__nv_bfloat16>::load(pr + d);
+      const float4 f = Vec4<T>::load(x + d), g = load_acc_slots(a + d, slots, sstride), q = Vec4<__nv_bfloat16>::load(pr + d);
       float4 r;
       r.x = (fmaf(c, q.x, g.x) - f.x * inv * dot) * inv;
       r.y = (fmaf(c, q.y, g.y) - f.y * inv * dot) * inv;
@@ -380,9 +531,11 @@ normalize_bwd_kernel(const T* __restrict__ X, int rows, int D, const float* __re
       r.w = (fmaf(c, q.w, g.w) - f.w * inv * dot) * inv;
       Vec4<T>::store(o + d, r);
     } else {
-      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), a[d]) - to_f32(x[d]) * inv * dot) * inv);
+      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), load_acc_slots1(a + d, slots, sstride)) - to_f32(x[d]) * inv * dot) * inv);
     }
   });
+  }  // row < rows
+  if (job.dt_out != nullptr) reduce_rowdot_last_block(job.rowdot, rows, job.ticket, job.dt_out);
 }
 
 // ------------------------------------------------------------------ register-resident variants (D = nch * 128 <= 1024)
@@ -393,8 +546,10 @@ constexpr int ROW_REG_CHUNKS = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-normalize_cast_reg_kernel(const T* __restrict__ X, int rows, int nch, __nv_bfloat16* __restrict__ Xn,
-                          float* __restrict__ inv_norm) {
+normalize_cast_reg_kernel(const NormalizeJob job, int rows, int nch) {
+  const T* __restrict__ X = static_cast<const T*>(job.X[blockIdx.y]);
+  __nv_bfloat16* __restrict__ Xn = job.Xn[blockIdx.y];
+  float* __restrict__ inv_norm = job.inv_norm[blockIdx.y];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -420,14 +575,22 @@ normalize_cast_reg_kernel(const T* __restrict__ X, int rows, int nch, __nv_bfloa
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-normalize_bwd_reg_kernel(const T* __restrict__ X, int rows, int nch, const float* __restrict__ inv_norm,
-                         const float* __restrict__ acc, const __nv_bfloat16* __restrict__ partner,
-                         long long partner_offset, const float* __restrict__ gdiag, const float* __restrict__ t_dev,
-                         const float* __restrict__ gamma_dev, float inv_rows, T* __restrict__ dX,
-                         float* __restrict__ rowdot) {
+normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* __restrict__ gdiag,
+                         const float* __restrict__ t_dev, const float* __restrict__ gamma_dev, float inv_rows) {
+  const int jy = blockIdx.y;
+  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
+  const float* __restrict__ inv_norm = job.inv_norm[jy];
+  const float* __restrict__ acc = job.acc[jy];
+  const __nv_bfloat16* __restrict__ partner = job.partner[jy];
+  const long long partner_offset = job.partner_offset[jy];
+  T* __restrict__ dX = static_cast<T*>(job.dX[jy]);
+  float* __restrict__ rowdot = jy == 0 ? job.rowdot : nullptr;
+  const int slots = job.acc_slots;
+  const long long sstride = job.acc_slot_stride;
+  normbwd_wait_peers(job);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (row < rows) {
   const int D = nch * 128;
   const float gamma = gamma_dev ? *gamma_dev : 1.f;
   const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
@@ -440,7 +603,7 @@ normalize_bwd_reg_kernel(const T* __restrict__ X, int rows, int nch, const float
   for (int i = 0; i < ROW_REG_CHUNKS; ++i)
     if (i < nch) {
       xv[i] = Vec4<T>::load(x + i * 128);
-      const float4 g = Vec4<float>::load(a + i * 128);
+      const float4 g = load_acc_slots(a + i * 128, slots, sstride);
       const float4 q = Vec4<__nv_bfloat16>::load(pr + i * 128);
       dv[i] = make_float4(fmaf(c, q.x, g.x), fmaf(c, q.y, g.y), fmaf(c, q.z, g.z), fmaf(c, q.w, g.w));   // dU
     }
@@ -462,50 +625,8 @@ normalize_bwd_reg_kernel(const T* __restrict__ X, int rows, int nch, const float
       r.w = (dv[i].w - xv[i].w * k) * inv;
       Vec4<T>::store(o + i * 128, r);
     }
-}
-
-// Dense-mode loss: partials rows = {sum softplus(-x_pos), sum max(s, 0), sum log2(1 + e), -} per epilogue warp.
-//   pos = P0 / M,   neg = (tau * P1 + ln2 * P2) / (M (N - 1)),   out4 = {pos, neg, pos + neg, 0}
-// (dL/dt of the dense mode is produced by the backward: it is the sum of the row dots <u_i, dU_i>.)
-__global__ void __launch_bounds__(FINALIZE_THREADS)
-finalize_dense_kernel(const float* __restrict__ partials, int n, double inv_pos, double inv_neg,
-                      const float* __restrict__ t_dev, float* __restrict__ out4, float* __restrict__ loss_out) {
-  __shared__ double sh[3][FINALIZE_THREADS];
-  double acc[3] = {0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS)
-    for (int k = 0; k < 3; ++k) acc[k] += (double)partials[(size_t)i * 4 + k];
-  for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = acc[k];
-  __syncthreads();
-  for (int s = FINALIZE_THREADS / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s)
-      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double tau = exp((double)*t_dev);
-    const double pos = sh[0][0] * inv_pos;
-    const double neg = (tau * sh[1][0] + 0.6931471805599453 * sh[2][0]) * inv_neg;
-    out4[0] = (float)pos;
-    out4[1] = (float)neg;
-    out4[2] = (float)(pos + neg);
-    out4[3] = 0.f;
-    if (loss_out) *loss_out = (float)(pos + neg);
-  }
-}
-
-// out = scale_dev * sum(x[0..n)) in a fixed order (fp64): dL/dt = sum_i <u_i, dU_i> of the dense backward
-__global__ void __launch_bounds__(FINALIZE_THREADS)
-sum_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
-  __shared__ double sh[FINALIZE_THREADS];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS) acc += (double)x[i];
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = FINALIZE_THREADS / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *out = (float)sh[0];
+  }  // row < rows
+  if (job.dt_out != nullptr) reduce_rowdot_last_block(job.rowdot, rows, job.ticket, job.dt_out);
 }
 
 }  // namespace jsd

@@ -93,6 +93,35 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---------------------------------------------------------------- system-scope flags (peer GPUs over NVLink)
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy observations (the flag) ordered before later async-proxy (TMA) accesses of global memory
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// Spin until every flag[0..count) has reached `target` (flags only grow); traps after 20 s instead of hanging.
+__device__ __forceinline__ void wait_flags_sys(const int* flags, int count, int target) {
+  for (int i = 0; i < count; ++i) {
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (ld_acquire_sys(flags + i) - target < 0) {
+      if ((++spins & 0xFFu) == 0) {
+        __nanosleep(200);
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -120,6 +120,20 @@ def streamk_workspace(device) -> torch.Tensor:
     return ws
 
 
+_FWD_WORKSPACES = {}
+
+
+def dense_workspace(device) -> torch.Tensor:
+    """Per (device, stream) scratch of the forward kernel: a finalisation ticket (must be zero between
+    launches; the kernel re-zeroes it) followed by the per-warp loss partials.  Allocated zeroed once."""
+    key = (str(device), _stream())
+    ws = _FWD_WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.load().jsd_dense_workspace_bytes(), dtype=torch.uint8, device=device)
+        _FWD_WORKSPACES[key] = ws
+    return ws
+
+
 def normalize_cast(x: torch.Tensor):
     """(Xn bf16 [rows, D], inv_norm fp32 [rows])."""
     _req(x, "X", ndim=2)
@@ -140,8 +154,6 @@ def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int
     if d != d2:
         raise ValueError(f"U and V disagree on D: {d} vs {d2}")
     tt = _scalar(t, "temperature")
-    lib = _lib.load()
-    ws = torch.empty(lib.jsd_dense_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
     out4 = torch.empty(4, dtype=torch.float32, device=u.device)
     loss = torch.empty((), dtype=torch.float32, device=u.device)
     gdiag = torch.empty(m, dtype=torch.float32, device=u.device)
@@ -151,6 +163,7 @@ def dense_fwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor, row_offset: int
         ldg = round_up(n, 64)
         gmat = torch.empty(m, ldg, dtype=torch.bfloat16, device=u.device)
     with _on_device(u.device):
+        ws = dense_workspace(u.device)
         _lib.call("jsd_dense_fwd", _ptr(u), _ptr(v), m, n, d, row_offset, _ptr(tt), _ptr(gmat), ldg, _ptr(gdiag),
                   _ptr(ws), _ptr(out4), _ptr(loss), _stream())
     return out4, loss, gmat, gdiag
@@ -163,19 +176,18 @@ def dense_forward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, want_grad: 
     b, d = f.shape
     dev = f.device
     tt = _scalar(t, "temperature")
-    lib = _lib.load()
     u = torch.empty(b, d, dtype=torch.bfloat16, device=dev)
     v = torch.empty(b, d, dtype=torch.bfloat16, device=dev)
-    # one fp32 allocation for the small vectors: inv_f | inv_g | gdiag | out4 | loss | partials workspace
-    nws = lib.jsd_dense_workspace_bytes() // 4
-    small = torch.empty(3 * b + 8 + nws, dtype=torch.float32, device=dev)
+    # one fp32 allocation for the small vectors: inv_f | inv_g | gdiag | out4 | loss
+    small = torch.empty(3 * b + 8, dtype=torch.float32, device=dev)
     inv_f, inv_g, gdiag = small[:b], small[b:2 * b], small[2 * b:3 * b]
-    out4, loss, ws = small[3 * b:3 * b + 4], small[3 * b + 4], small[3 * b + 8:]
+    out4, loss = small[3 * b:3 * b + 4], small[3 * b + 4]
     gmat, ldg = None, 0
     if want_grad:
         ldg = round_up(b, 64)
         gmat = torch.empty(b, ldg, dtype=torch.bfloat16, device=dev)
     with _on_device(dev):
+        ws = dense_workspace(dev)
         _lib.call("jsd_dense_forward", f.data_ptr(), g.data_ptr(), _code(f), b, d, tt.data_ptr(), u.data_ptr(),
                   v.data_ptr(), inv_f.data_ptr(), inv_g.data_ptr(), _ptr(gmat), ldg, gdiag.data_ptr(),
                   ws.data_ptr(), out4.data_ptr(), loss.data_ptr(), _stream())
@@ -194,10 +206,11 @@ def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: tor
     dg = torch.empty_like(g)
     small = torch.empty(b + 1, dtype=torch.float32, device=dev)       # row dots | dt
     with _on_device(dev):
+        ws = dense_workspace(dev)
         _lib.call("jsd_dense_backward", f.data_ptr(), g.data_ptr(), _code(f), b, d, u.data_ptr(), v.data_ptr(),
                   inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
                   tt.data_ptr(), gg.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(), small.data_ptr(),
-                  df.data_ptr(), dg.data_ptr(), small[b:].data_ptr(), _stream())
+                  ws.data_ptr(), df.data_ptr(), dg.data_ptr(), small[b:].data_ptr(), _stream())
     return df, dg, small[b]
 
 
@@ -251,10 +264,10 @@ def normalize_bwd(x: torch.Tensor, inv_norm: torch.Tensor, acc: torch.Tensor, pa
     dx = torch.empty_like(x)
     rowdot = torch.empty(rows + 1, dtype=torch.float32, device=x.device) if want_dt else None
     with _on_device(x.device):
+        ws = dense_workspace(x.device) if want_dt else None
         _lib.call("jsd_normalize_bwd", _ptr(x), _code(x), rows, d, _ptr(inv_norm), _ptr(acc), _ptr(partner),
-                  partner_offset, _ptr(gdiag), _ptr(tt), _ptr(gg), m_rows, _ptr(dx), _ptr(rowdot), _stream())
-        if want_dt:
-            _lib.call("jsd_sum_f32", rowdot.data_ptr(), rows, rowdot[rows:].data_ptr(), _stream())
+                  partner_offset, _ptr(gdiag), _ptr(tt), _ptr(gg), m_rows, _ptr(dx), _ptr(rowdot), _ptr(ws),
+                  rowdot[rows:].data_ptr() if want_dt else None, _stream())
     return (dx, rowdot[rows]) if want_dt else dx
 
 
@@ -282,9 +295,10 @@ def dense_backward_image_side(f, v_all, inv_f, gmat, gdiag, t, gamma, row_offset
     small = torch.empty(m + 1, dtype=torch.float32, device=dev)
     df = torch.empty_like(f)
     with _on_device(dev):
+        ws = dense_workspace(dev)
         _lib.call("jsd_dense_backward_image_side", f.data_ptr(), _code(f), m, n, d, row_offset, v_all.data_ptr(),
                   inv_f.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(), tt.data_ptr(), gg.data_ptr(),
-                  acc.data_ptr(), small.data_ptr(), df.data_ptr(), small[m:].data_ptr(), _stream())
+                  acc.data_ptr(), small.data_ptr(), ws.data_ptr(), df.data_ptr(), small[m:].data_ptr(), _stream())
     return df, small[m]
 
 

@@ -72,6 +72,10 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
 int jsd_normalize_cast(const void* X, int dtype, int64_t rows, int64_t D, void* Xn_bf16, float* inv_norm,
                        jsd_stream_t stream);
 
+/* Scratch of the dense path: 16 bytes of "last block" tickets (word 0: loss finalisation of jsd_dense_fwd,
+ * word 1: dL/dt reduction of jsd_normalize_bwd) followed by the per-warp loss partials.  The tickets must be
+ * ZERO when the buffer is first used; every launch leaves them zero again (the last CTA to finish does the
+ * reduction -- no separate reduction launch).  One buffer per concurrently used stream. */
 size_t jsd_dense_workspace_bytes(void);
 
 /* Forward: S = tau U V^T on tcgen05 tensor cores, softplus/sigmoid epilogue, S never stored.
@@ -107,37 +111,90 @@ int jsd_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, int
  *   d_row = acc_row + gamma tau / M_rows * gdiag[row] * partner[row + partner_offset]
  *   dX_row = (d_row - u_row <u_row, d_row>) * inv_norm[row],   u_row = X_row * inv_norm[row]
  * X, dX [rows, D] in `dtype`; acc fp32 [rows, D]; partner bf16 [*, D]; gdiag may be NULL (no positive term).
- * rowdot (optional, may be NULL) [rows] receives <u_row, d_row>; summed over the image rows it is
- * gamma * dL/dt (jsd_sum_f32 reduces it in a fixed order). */
+ * rowdot (optional, may be NULL) [rows] receives <u_row, d_row>.  dt_out (optional; needs rowdot and the forward's
+ * `workspace`, whose second ticket word serialises it) receives sum_rows rowdot = gamma * dL/dt when X are the
+ * image rows: the last block of the same launch reduces the row dots in a fixed order (fp64, deterministic). */
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner_bf16, int64_t partner_offset, const float* gdiag, const float* t_dev,
-                      const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, jsd_stream_t stream);
-int jsd_sum_f32(const float* x, int64_t n, float* out, jsd_stream_t stream);
+                      const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, void* workspace, float* dt_out,
+                      jsd_stream_t stream);
 
 /* Single-GPU convenience (M == N == B, row_offset 0): the whole forward, resp. the whole backward, in
- * one call, so that the host pays one FFI crossing per autograd direction.
- *   forward : jsd_normalize_cast(F) , jsd_normalize_cast(G), jsd_dense_fwd
- *   backward: jsd_dense_bwd_du, jsd_dense_bwd_dv, jsd_normalize_bwd x2, dt_out = jsd_sum_f32(rowdot)
+ * one call, so that the host pays one FFI crossing per autograd direction (2 + 3 kernel launches per step).
+ *   forward : jsd_normalize_cast_pair(F, G), jsd_dense_fwd (loss reduced by its last CTA)
+ *   backward: jsd_dense_bwd_du, jsd_dense_bwd_dv, ONE launch for both jsd_normalize_bwd's and dt_out
  * F, G [B, D] in `dtype`; U, V bf16 [B, D]; acc_u, acc_v fp32 [B, D] and rowdot fp32 [B] scratch;
- * dF, dG in `dtype`; dt_out = gamma * dL/dt. */
+ * workspace = the forward's; dF, dG in `dtype`; dt_out = gamma * dL/dt. */
 int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U_bf16,
                       void* V_bf16, float* inv_f, float* inv_g, void* Gmat_bf16, int64_t ldg, float* gdiag,
                       void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
 int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U_bf16,
                        const void* V_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16, int64_t ldg,
                        const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v,
-                       float* rowdot, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
+                       float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
 /* Row-slab (multi-GPU) convenience calls: one FFI crossing each.
- *   jsd_normalize_cast_pair       = jsd_normalize_cast(F) , jsd_normalize_cast(G)
+ *   jsd_normalize_cast_pair       = jsd_normalize_cast of F and of G in one launch
  *   jsd_dense_backward_image_side = jsd_dense_bwd_du, jsd_normalize_bwd (positives at column row_offset + i of
- *                                   V_all, row dots), dt_out = jsd_sum_f32(rowdot) = gamma * dL_r/dt */
+ *                                   V_all, row dots, dt_out = gamma * dL_r/dt) */
 int jsd_normalize_cast_pair(const void* F, const void* G, int dtype, int64_t rows, int64_t D, void* U_bf16,
                             void* V_bf16, float* inv_f, float* inv_g, jsd_stream_t stream);
 int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                                   const void* V_all_bf16, const float* inv_f, const void* Gmat_bf16, int64_t ldg,
                                   const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                                  float* rowdot, void* dF, float* dt_out, jsd_stream_t stream);
+                                  float* rowdot, void* workspace, void* dF, float* dt_out, jsd_stream_t stream);
+
+/* ------------------------------------------------------------------ peer-memory exchange (multi-GPU dense path)
+ * One process per GPU; the two exchange steps of the sharded path (all-gather of the text rows, sum of
+ * the dV partials on the owner rank) are fused into the kernels that produce / consume the data, over NVLink peer
+ * memory, instead of separate NCCL collectives:
+ *   jsd_peer_normalize_push      normalises F -> local U, G -> V rows stored into EVERY rank's gathered V buffer
+ *   jsd_peer_dense_fwd           jsd_dense_fwd on (U, this rank's gathered V); its TMA producer first waits for
+ *                                every rank's "rows are in" flag
+ *   jsd_peer_dense_bwd_dv        dV partial tiles stored straight into the owner rank's staging slot
+ *   jsd_peer_normalize_bwd_text  waits for every rank's "partials are in" flag, sums the `world` slots in rank
+ *                                order (deterministic), positive-pair term, Jacobian of F.normalize
+ * (the image side uses jsd_dense_backward_image_side with V_all = v_all[parity][rank]).
+ * Buffers come from jsd_peer_alloc (cudaMalloc, zero-filled) and are mapped into the other processes with
+ * jsd_peer_export / jsd_peer_open (CUDA IPC).  The gathered V buffer is double-buffered by the step's parity
+ * (the caller alternates 0, 1, 0, ...; every rank must use the same sequence), so a rank may start pushing step
+ * k+1 while a slower rank still reads step k.  Flags only grow (per-buffer push counters): nothing is reset.
+ * Every rank must make the same sequence of calls (collective semantics), one step in flight at a time. */
+#define JSD_MAX_PEERS 8
+#define JSD_PEER_HANDLE_BYTES 64
+/* layout of a rank's flag block (int32 words) */
+#define JSD_PEER_READY_V 0        /* [parity][source rank]: pushes of that rank into this rank's V buffer */
+#define JSD_PEER_READY_DV 16      /* [source rank]: dV partial launches of that rank */
+#define JSD_PEER_COUNTER_V 24     /* [parity] this rank's own push counter */
+#define JSD_PEER_COUNTER_DV 26
+#define JSD_PEER_TICKET_PUSH 27
+#define JSD_PEER_TICKET_DV 28
+#define JSD_PEER_FLAG_INTS 32
+
+typedef struct jsd_peer_ctx {
+  int32_t rank, world;
+  int64_t rows;                          /* rows per rank (the same on every rank) */
+  int64_t dim;                           /* D */
+  void* v_all[2][JSD_MAX_PEERS];         /* [parity][q]: rank q's gathered V [world * rows, D] bf16, as mapped here */
+  void* stage[JSD_MAX_PEERS];            /* rank q's staging [world, rows, D] fp32 */
+  int32_t* flags[JSD_MAX_PEERS];         /* rank q's flag block, zero before the first step */
+} jsd_peer_ctx;
+
+size_t jsd_peer_flag_bytes(void);
+int jsd_peer_alloc(size_t bytes, void** out_ptr);
+int jsd_peer_free(void* ptr);
+int jsd_peer_export(void* ptr, void* handle64);
+int jsd_peer_open(const void* handle64, void** out_ptr);
+int jsd_peer_close(void* ptr);
+int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity, void* U_bf16,
+                            float* inv_f, float* inv_g, jsd_stream_t stream);
+int jsd_peer_dense_fwd(const void* U_bf16, const jsd_peer_ctx* ctx, int parity, const float* t_dev, void* Gmat_bf16,
+                       int64_t ldg, float* gdiag, void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
+int jsd_peer_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, const jsd_peer_ctx* ctx,
+                          const float* t_dev, const float* gamma_dev, jsd_stream_t stream);
+int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g,
+                                const void* U_bf16, const float* gdiag, const float* t_dev, const float* gamma_dev,
+                                void* dG, jsd_stream_t stream);
 
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or

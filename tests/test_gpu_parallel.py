@@ -67,3 +67,68 @@ def test_gathered_dense_matches_single_gpu(world):
         assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
         tot_dt += float(gt)
     assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
+
+
+# ------------------------------------------------------------------ peer-memory exchange (no NCCL on the data path)
+def _peer_worker(rank, world, port, results):
+    from clip_lite_b200 import peer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m = B // world
+        t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
+        out = []
+        # three eager steps on different data (both parities of the double-buffered gathered V, flags re-used)
+        for seed in (0, 1, 2):
+            f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+            fl = f[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
+            gl = g[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
+            t.grad = None
+            loss, _ = peer.peer_dense_loss(fl, gl, t)
+            (0.5 * loss).backward()
+            torch.cuda.synchronize()
+            out.append(tuple(x.detach().cpu() for x in (loss, fl.grad, gl.grad, t.grad)))
+        # forward only (no backward between two forwards) must not disturb the exchange
+        with torch.no_grad():
+            l_eval, _ = peer.peer_dense_loss(fl.detach(), gl.detach(), t.detach())
+            l_eval2, _ = peer.peer_dense_loss(fl.detach(), gl.detach(), t.detach())
+        torch.cuda.synchronize()
+        assert float(l_eval) == float(l_eval2) == float(out[-1][0])
+        # graphed replay: two graphs (one per parity), several replays on the seed-2 data, bit-identical to eager
+        gs = peer.PeerGraphedStep(fl.detach(), gl.detach(), t.detach())
+        gs.gamma.fill_(0.5)
+        for _ in range(5):
+            l2, df2, dg2, dt2 = gs()
+        torch.cuda.synchronize()
+        out.append(tuple(x.detach().cpu().clone() for x in (l2, df2, dg2, dt2)))
+        results[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_exchange_matches_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    m = B // world
+    for si, seed in enumerate((0, 1, 2)):
+        f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+        fd, gd = f.double(), g.double()
+        df, dg, dt = orc.jsd_dense_grads(fd, gd, orc.T_INIT, gamma=0.5)
+        tot_dt = 0.0
+        for r in range(world):
+            loss, gf, gg, gt = results[r][si]
+            slab = orc.jsd_dense(fd[r * m:(r + 1) * m], gd, orc.T_INIT, row_offset=r * m)
+            assert abs(float(loss) - float(slab["loss"])) < 1e-3 * float(slab["loss"])
+            ref_f, ref_g = world * df[r * m:(r + 1) * m], world * dg[r * m:(r + 1) * m]
+            assert (gf.double() - ref_f).abs().max() < 1e-2 * ref_f.abs().max()
+            assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
+            tot_dt += float(gt)
+        assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
+    for r in range(world):      # graph replay == eager on the same data (deterministic kernels, fixed slot order)
+        for a, b in zip(results[r][2], results[r][3]):
+            assert torch.equal(a, b)

@@ -216,6 +216,7 @@ int launch_normalize_bwd(const jsd::NormBwdJob& job, int count, int64_t rows, in
   for (int i = 0; i < count; ++i)
     bits |= reinterpret_cast<uintptr_t>(job.X[i]) | reinterpret_cast<uintptr_t>(job.dX[i]) |
             reinterpret_cast<uintptr_t>(job.acc[i]) | reinterpret_cast<uintptr_t>(job.partner[i]);
+  for (int q = 0; q < job.acc_slots; ++q) bits |= reinterpret_cast<uintptr_t>(job.slot[q]);
   const bool vec = (D % 4 == 0) && (bits & 15) == 0;
   const dim3 grid((unsigned)((rows + 7) / 8), (unsigned)count);
   if (vec && D % 128 == 0 && D / 128 <= jsd::ROW_REG_CHUNKS)
@@ -415,15 +416,12 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
   p.out = out;
   p.ldo = D;
   if (peer != nullptr) {
-    // rows of dV_all are global text rows: row j belongs to rank j / rows_per_rank, which receives this rank's
-    // fp32 partial in slot `rank` of its staging buffer
-    p.peer_rows = (int)peer->rows;
+    // the partial over ALL text rows stays in this rank's (peer-mapped) buffer; the owner of each row block
+    // reads it from there once this launch has published its flag
+    p.out = (float*)peer->stage[peer->rank];
     p.peer_world = peer->world;
     int32_t* mine = peer->flags[peer->rank];
-    for (int q = 0; q < peer->world; ++q) {
-      p.peer_out[q] = (float*)peer->stage[q] + (size_t)peer->rank * peer->rows * D;
-      p.peer_flag_dst[q] = peer->flags[q] + JSD_PEER_READY_DV + peer->rank;
-    }
+    for (int q = 0; q < peer->world; ++q) p.peer_flag_dst[q] = peer->flags[q] + JSD_PEER_READY_DV + peer->rank;
     p.peer_counter = mine + JSD_PEER_COUNTER_DV;
     p.peer_ticket = mine + JSD_PEER_TICKET_DV;
   }
@@ -628,12 +626,12 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
   jsd::NormBwdJob job{};
   job.X[0] = G;
   job.inv_norm[0] = inv_g;
-  job.acc[0] = (const float*)ctx->stage[ctx->rank];
   job.partner[0] = (const __nv_bfloat16*)U;
   job.partner_offset[0] = 0;
   job.dX[0] = dG;
   job.acc_slots = ctx->world;
-  job.acc_slot_stride = (long long)ctx->rows * ctx->dim;
+  for (int q = 0; q < ctx->world; ++q)        // rank q's partial, rows of this rank
+    job.slot[q] = (const float*)ctx->stage[q] + (size_t)ctx->rank * ctx->rows * ctx->dim;
   job.wait_flags = mine + JSD_PEER_READY_DV;
   job.wait_counter = mine + JSD_PEER_COUNTER_DV;
   job.wait_count = ctx->world;

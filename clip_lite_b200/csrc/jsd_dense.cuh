@@ -107,16 +107,14 @@ struct GemmParams {
   int stream_k;
   int* sk_flags;
   float* sk_slots;
-  // peer-memory exchange (multi-GPU, see jsd_peer.cuh).  wait_*: the TMA producer holds its first load until every
-  // rank's flag has reached *wait_counter (the gathered B operand was written by peer GPUs).  peer_*: GRAD
-  // epilogue stores row r of the output into rank (r / peer_rows)'s buffer (peer_out[q], row r % peer_rows); the
-  // last CTA of the launch then bumps *peer_counter and publishes it to every rank's flag (system scope).
+  // peer-memory exchange (multi-GPU).  wait_*: the TMA producer holds its first load until every rank's flag has
+  // reached *wait_counter (the gathered B operand was written by peer GPUs).  peer_*: the output of a GRAD launch
+  // is read by the other ranks straight out of this GPU's memory; the last CTA of the launch bumps *peer_counter
+  // and publishes it to every rank's flag (system scope) once all CTAs' stores are fenced.
   const int* wait_flags;
   const int* wait_counter;
   int wait_count;
-  int peer_rows;                 // 0 = plain local output
-  int peer_world;
-  float* peer_out[MAX_PEERS];
+  int peer_world;                // 0 = nobody to notify
   int* peer_flag_dst[MAX_PEERS];
   int* peer_counter;
   int* peer_ticket;
@@ -537,13 +535,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (row_ok) {
-            float* dst;
-            if (p.peer_rows > 0) {           // the row's owner rank receives this rank's partial (NVLink store)
-              const int owner = grow / p.peer_rows;
-              dst = p.peer_out[owner] + (long long)(grow - owner * p.peer_rows) * p.ldo + col0;
-            } else {
-              dst = p.out + (long long)grow * p.ldo + col0;
-            }
+            float* dst = p.out + (long long)grow * p.ldo + col0;
             if (col0 + CW <= p.N) {
 #pragma unroll
               for (int k4 = 0; k4 < CW / 4; ++k4) {
@@ -620,7 +612,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     if constexpr (MODE == MODE_GRAD) {
-      if (p.peer_rows > 0) __threadfence_system();   // this thread's peer stores, before the CTA takes its ticket
+      if (p.peer_world > 0) __threadfence_system();   // this thread's stores, before the CTA takes its ticket
     }
     if constexpr (MODE == MODE_FWD) {
       if (p.gmat != nullptr && lane == 0) tma_store_wait_all();   // smem must outlive the last store
@@ -647,8 +639,8 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   if constexpr (MODE == MODE_GRAD) {
-    // Peer exchange: once every CTA's stores are fenced, the last CTA publishes "this rank's partials are in".
-    if (p.peer_rows > 0) {
+    // Peer exchange: once every CTA's stores are fenced, the last CTA publishes "this rank's partial is complete".
+    if (p.peer_world > 0) {
       int* s_last = reinterpret_cast<int*>(smem_raw);
       if (threadIdx.x == 0) {
         __threadfence_system();

@@ -316,9 +316,10 @@ struct NormalizeJob {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 normalize_cast_kernel(const NormalizeJob job, int rows, int D) {
-  const T* __restrict__ X = static_cast<const T*>(job.X[blockIdx.y]);
-  __nv_bfloat16* __restrict__ Xn = job.Xn[blockIdx.y];
-  float* __restrict__ inv_norm = job.inv_norm[blockIdx.y];
+  const bool second = blockIdx.y != 0;      // static selects: a dynamically indexed parameter array goes through local memory
+  const T* __restrict__ X = static_cast<const T*>(second ? job.X[1] : job.X[0]);
+  __nv_bfloat16* __restrict__ Xn = second ? job.Xn[1] : job.Xn[0];
+  float* __restrict__ inv_norm = second ? job.inv_norm[1] : job.inv_norm[0];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -418,8 +419,7 @@ normalize_push_kernel(const PeerPushJob job, int rows, int D) {
 __device__ __forceinline__ void reduce_rowdot_last_block(const float* rowdot, int rows, int* ticket, float* dt_out) {
   __shared__ int s_last;
   __shared__ double s_part[256];
-  __threadfence();                                   // this block's rowdot entries
-  __syncthreads();
+  __syncthreads();                                   // every warp has stored AND fenced its rowdot entry
   if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
   __syncthreads();
   if (!s_last) return;
@@ -455,11 +455,12 @@ struct NormBwdJob {
   float* rowdot;     // job 0 only; may be null
   int* ticket;       // zero between launches (needed iff dt_out != nullptr)
   float* dt_out;     // may be null
-  // peer exchange (text side of a multi-GPU step): acc is `acc_slots` partial accumulators, `acc_slot_stride`
-  // floats apart, one per rank, summed here in rank order (deterministic); every block first waits until each
-  // rank's flag has reached *wait_counter ("my partial is in your buffer").
-  int acc_slots;               // <= 1: a single accumulator
-  long long acc_slot_stride;
+  // peer exchange (text side of a multi-GPU step): the accumulator is the sum of `acc_slots` partials, one in
+  // each rank's memory (slot[q], read over NVLink, already offset to this rank's rows), added here in rank order
+  // (deterministic) -- the reduce-scatter is fused into its consumer.  Every block first waits until each rank's
+  // flag has reached *wait_counter ("my partial is complete").
+  int acc_slots;               // 0: a single local accumulator (acc[])
+  const float* slot[8];
   const int* wait_flags;       // null: no wait
   const int* wait_counter;
   int wait_count;
@@ -471,17 +472,25 @@ __device__ __forceinline__ void normbwd_wait_peers(const NormBwdJob& job) {
   __syncthreads();
 }
 
-__device__ __forceinline__ float4 load_acc_slots(const float* a, int slots, long long stride) {
-  float4 g = __ldcg(reinterpret_cast<const float4*>(a));
-  for (int sl = 1; sl < slots; ++sl) {
-    const float4 h = __ldcg(reinterpret_cast<const float4*>(a + sl * stride));
-    g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
-  }
+// accumulator element(s) at float offset `off` of the row block: the single local accumulator, or the sum over
+// the ranks' partials in rank order
+__device__ __forceinline__ float4 load_acc4(const NormBwdJob& job, const float* acc, size_t off) {
+  if (job.acc_slots <= 0) return __ldcs(reinterpret_cast<const float4*>(acc + off));
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int sl = 0; sl < 8; ++sl)
+    if (sl < job.acc_slots) {
+      const float4 h = __ldcs(reinterpret_cast<const float4*>(job.slot[sl] + off));
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
   return g;
 }
-__device__ __forceinline__ float load_acc_slots1(const float* a, int slots, long long stride) {
-  float g = __ldcg(a);
-  for (int sl = 1; sl < slots; ++sl) g += __ldcg(a + sl * stride);
+__device__ __forceinline__ float load_acc1(const NormBwdJob& job, const float* acc, size_t off) {
+  if (job.acc_slots <= 0) return acc[off];
+  float g = 0.f;
+#pragma unroll
+  for (int sl = 0; sl < 8; ++sl)
+    if (sl < job.acc_slots) g += job.slot[sl][off];
   return g;
 }
 
@@ -489,16 +498,14 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restrict__ gdiag,
                      const float* __restrict__ t_dev, const float* __restrict__ gamma_dev, float inv_rows) {
-  const int jy = blockIdx.y;
-  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
-  const float* __restrict__ inv_norm = job.inv_norm[jy];
-  const float* __restrict__ acc = job.acc[jy];
-  const __nv_bfloat16* __restrict__ partner = job.partner[jy];
-  const long long partner_offset = job.partner_offset[jy];
-  T* __restrict__ dX = static_cast<T*>(job.dX[jy]);
-  float* __restrict__ rowdot = jy == 0 ? job.rowdot : nullptr;
-  const int slots = job.acc_slots;
-  const long long sstride = job.acc_slot_stride;
+  const bool second = blockIdx.y != 0;
+  const T* __restrict__ X = static_cast<const T*>(second ? job.X[1] : job.X[0]);
+  const float* __restrict__ inv_norm = second ? job.inv_norm[1] : job.inv_norm[0];
+  const float* __restrict__ acc = second ? job.acc[1] : job.acc[0];
+  const __nv_bfloat16* __restrict__ partner = second ? job.partner[1] : job.partner[0];
+  const long long partner_offset = second ? job.partner_offset[1] : job.partner_offset[0];
+  T* __restrict__ dX = static_cast<T*>(second ? job.dX[1] : job.dX[0]);
+  float* __restrict__ rowdot = second ? nullptr : job.rowdot;
   normbwd_wait_peers(job);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -507,23 +514,26 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
   const float inv = inv_norm[row];
   const T* x = X + (size_t)row * D;
-  const float* a = acc + (size_t)row * D;
+  const size_t aoff = (size_t)row * D;
   const __nv_bfloat16* pr = partner + (size_t)(row + partner_offset) * D;
   float dot = 0.f;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
-      const float4 f = Vec4<T>::load(x + d), g = load_acc_slots(a + d, slots, sstride), q = Vec4<__nv_bfloat16>::load(pr + d);
+      const float4 f = Vec4<T>::load(x + d), g = load_acc4(job, acc, aoff + d), q = Vec4<__nv_bfloat16>::load(pr + d);
       dot += f.x * fmaf(c, q.x, g.x) + f.y * fmaf(c, q.y, g.y) + f.z * fmaf(c, q.z, g.z) + f.w * fmaf(c, q.w, g.w);
     } else {
-      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), load_acc_slots1(a + d, slots, sstride));
+      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), load_acc1(job, acc, aoff + d));
     }
   });
   dot = warp_sum(dot) * inv;   // <u, dU>
-  if (rowdot != nullptr && lane == 0) rowdot[row] = dot;   // sum over rows = gamma * dL/dt
+  if (rowdot != nullptr && lane == 0) {   // sum over rows = gamma * dL/dt
+    rowdot[row] = dot;
+    __threadfence();                      // published now: the fence must not wait for the row's big stores below
+  }
   T* o = dX + (size_t)row * D;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
-      const float4 f = Vec4<T>::load(x + d), g = load_acc_slots(a + d, slots, sstride), q = Vec4<__nv_bfloat16>::load(pr + d);
+      const float4 f = Vec4<T>::load(x + d), g = load_acc4(job, acc, aoff + d), q = Vec4<__nv_bfloat16>::load(pr + d);
       float4 r;
       r.x = (fmaf(c, q.x, g.x) - f.x * inv * dot) * inv;
       r.y = (fmaf(c, q.y, g.y) - f.y * inv * dot) * inv;
@@ -531,7 +541,7 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
       r.w = (fmaf(c, q.w, g.w) - f.w * inv * dot) * inv;
       Vec4<T>::store(o + d, r);
     } else {
-      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), load_acc_slots1(a + d, slots, sstride)) - to_f32(x[d]) * inv * dot) * inv);
+      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), load_acc1(job, acc, aoff + d)) - to_f32(x[d]) * inv * dot) * inv);
     }
   });
   }  // row < rows
@@ -547,9 +557,10 @@ constexpr int ROW_REG_CHUNKS = 8;
 template <typename T>
 __global__ void __launch_bounds__(256)
 normalize_cast_reg_kernel(const NormalizeJob job, int rows, int nch) {
-  const T* __restrict__ X = static_cast<const T*>(job.X[blockIdx.y]);
-  __nv_bfloat16* __restrict__ Xn = job.Xn[blockIdx.y];
-  float* __restrict__ inv_norm = job.inv_norm[blockIdx.y];
+  const bool second = blockIdx.y != 0;      // static selects: a dynamically indexed parameter array goes through local memory
+  const T* __restrict__ X = static_cast<const T*>(second ? job.X[1] : job.X[0]);
+  __nv_bfloat16* __restrict__ Xn = second ? job.Xn[1] : job.Xn[0];
+  float* __restrict__ inv_norm = second ? job.inv_norm[1] : job.inv_norm[0];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -577,16 +588,14 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* __restrict__ gdiag,
                          const float* __restrict__ t_dev, const float* __restrict__ gamma_dev, float inv_rows) {
-  const int jy = blockIdx.y;
-  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
-  const float* __restrict__ inv_norm = job.inv_norm[jy];
-  const float* __restrict__ acc = job.acc[jy];
-  const __nv_bfloat16* __restrict__ partner = job.partner[jy];
-  const long long partner_offset = job.partner_offset[jy];
-  T* __restrict__ dX = static_cast<T*>(job.dX[jy]);
-  float* __restrict__ rowdot = jy == 0 ? job.rowdot : nullptr;
-  const int slots = job.acc_slots;
-  const long long sstride = job.acc_slot_stride;
+  const bool second = blockIdx.y != 0;
+  const T* __restrict__ X = static_cast<const T*>(second ? job.X[1] : job.X[0]);
+  const float* __restrict__ inv_norm = second ? job.inv_norm[1] : job.inv_norm[0];
+  const float* __restrict__ acc = second ? job.acc[1] : job.acc[0];
+  const __nv_bfloat16* __restrict__ partner = second ? job.partner[1] : job.partner[0];
+  const long long partner_offset = second ? job.partner_offset[1] : job.partner_offset[0];
+  T* __restrict__ dX = static_cast<T*>(second ? job.dX[1] : job.dX[0]);
+  float* __restrict__ rowdot = second ? nullptr : job.rowdot;
   normbwd_wait_peers(job);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -596,23 +605,49 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
   const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
   const float inv = inv_norm[row];
   const T* x = X + (size_t)row * D + lane * 4;
-  const float* a = acc + (size_t)row * D + lane * 4;
+  const size_t aoff = (size_t)row * D + lane * 4;
   const __nv_bfloat16* pr = partner + (size_t)(row + partner_offset) * D + lane * 4;
   float4 xv[ROW_REG_CHUNKS], dv[ROW_REG_CHUNKS];
+  // dv starts as the accumulator row (the sum of the ranks' partials in rank order when there are several); every
+  // chunk load of a pass is issued before the first use so that the whole row is in flight together
+  if (job.acc_slots <= 0) {
+#pragma unroll
+    for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+      if (i < nch) dv[i] = __ldcs(reinterpret_cast<const float4*>(acc + aoff + i * 128));
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROW_REG_CHUNKS; ++i) dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl)
+      if (sl < job.acc_slots) {
+        const float* a = job.slot[sl] + aoff;
+        float4 h[ROW_REG_CHUNKS];
+#pragma unroll
+        for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+          if (i < nch) h[i] = __ldcs(reinterpret_cast<const float4*>(a + i * 128));
+#pragma unroll
+        for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+          if (i < nch) {
+            dv[i].x += h[i].x; dv[i].y += h[i].y; dv[i].z += h[i].z; dv[i].w += h[i].w;
+          }
+      }
+  }
 #pragma unroll
   for (int i = 0; i < ROW_REG_CHUNKS; ++i)
     if (i < nch) {
       xv[i] = Vec4<T>::load(x + i * 128);
-      const float4 g = load_acc_slots(a + i * 128, slots, sstride);
       const float4 q = Vec4<__nv_bfloat16>::load(pr + i * 128);
-      dv[i] = make_float4(fmaf(c, q.x, g.x), fmaf(c, q.y, g.y), fmaf(c, q.z, g.z), fmaf(c, q.w, g.w));   // dU
+      dv[i] = make_float4(fmaf(c, q.x, dv[i].x), fmaf(c, q.y, dv[i].y), fmaf(c, q.z, dv[i].z), fmaf(c, q.w, dv[i].w));   // dU
     }
   float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < ROW_REG_CHUNKS; ++i)
     if (i < nch) dot += xv[i].x * dv[i].x + xv[i].y * dv[i].y + xv[i].z * dv[i].z + xv[i].w * dv[i].w;
   dot = warp_sum(dot) * inv;   // <u, dU>
-  if (rowdot != nullptr && lane == 0) rowdot[row] = dot;
+  if (rowdot != nullptr && lane == 0) {
+    rowdot[row] = dot;
+    __threadfence();                      // published now: the fence must not wait for the row's big stores below
+  }
   T* o = dX + (size_t)row * D + lane * 4;
   const float k = inv * dot;
 #pragma unroll

@@ -7,9 +7,10 @@ fused into the kernels on either side of them instead of being NCCL collectives:
   normalise + gather   the normalise kernel stores each bf16 text row into EVERY rank's gathered V buffer
                        (peer stores over NVLink) and publishes a flag; the forward's TMA producer waits for
                        the flags of all ranks before its first load.
-  dV + reduce          the epilogue of the dV contraction stores each fp32 partial tile straight into the
-                       owner rank's staging slot and publishes a flag; the owner's text-side Jacobian kernel
-                       waits for all flags and sums the slots in rank order (deterministic).
+  dV + reduce          the dV contraction leaves its fp32 partial (all text rows) in a peer-mapped buffer and
+                       publishes a flag; the owner's text-side Jacobian kernel waits for all flags, reads its
+                       rows of every rank's partial over NVLink (coalesced 512-byte row segments) and sums them
+                       in rank order (deterministic).
 
 A step is therefore five kernel launches and no collective call, which also makes the whole step
 capturable in a CUDA graph (``PeerGraphedStep``).  ``torch.distributed`` is used once, at set-up, to
@@ -180,9 +181,10 @@ class _PeerDenseFn(torch.autograd.Function):
         with torch.autocast(fc.device.type, enabled=False):
             gamma = grad_loss.float()
             v_all = ex.v_all[ctx.parity]
-            # image side first: when this rank's dV flag goes out, all its reads of the gathered V are done
-            df, dt = K.dense_backward_image_side(fc, v_all, inv_f, gmat, gdiag, t, gamma, ex.rank * ex.rows)
+            # text-side partial first: its flag goes out early and the peers' partials arrive while the
+            # image side computes (the gathered V is double-buffered, so the order is free)
             ex.dense_bwd_dv(gmat, u, t, gamma)
+            df, dt = K.dense_backward_image_side(fc, v_all, inv_f, gmat, gdiag, t, gamma, ex.rank * ex.rows)
             dg = ex.normalize_bwd_text(gc, inv_g, u, gdiag, t, gamma)
         fd, gd, td = ctx.dtypes
         return df.to(fd), dg.to(gd), dt.to(td), None
@@ -211,9 +213,9 @@ class PeerGraphedStep:
         def step(parity):
             u, inv_f, inv_g = ex.normalize_push(self.f, self.g, parity)
             out4, loss, gmat, gdiag = ex.dense_fwd(u, self.t, parity)
+            ex.dense_bwd_dv(gmat, u, self.t, self.gamma)
             df, dt = K.dense_backward_image_side(self.f, ex.v_all[parity], inv_f, gmat, gdiag, self.t, self.gamma,
                                                  ex.rank * ex.rows)
-            ex.dense_bwd_dv(gmat, u, self.t, self.gamma)
             dg = ex.normalize_bwd_text(self.g, inv_g, u, gdiag, self.t, self.gamma)
             return loss, df, dg, dt
 

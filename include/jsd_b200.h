@@ -151,9 +151,11 @@ int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N
  *   jsd_peer_normalize_push      normalises F -> local U, G -> V rows stored into EVERY rank's gathered V buffer
  *   jsd_peer_dense_fwd           jsd_dense_fwd on (U, this rank's gathered V); its TMA producer first waits for
  *                                every rank's "rows are in" flag
- *   jsd_peer_dense_bwd_dv        dV partial tiles stored straight into the owner rank's staging slot
- *   jsd_peer_normalize_bwd_text  waits for every rank's "partials are in" flag, sums the `world` slots in rank
- *                                order (deterministic), positive-pair term, Jacobian of F.normalize
+ *   jsd_peer_dense_bwd_dv        dV partial over all text rows into this rank's peer-mapped buffer; its last
+ *                                CTA publishes "partial complete" to every rank
+ *   jsd_peer_normalize_bwd_text  waits for every rank's flag, reads its rows of every rank's partial over NVLink
+ *                                and sums them in rank order (deterministic): the reduce-scatter is fused into
+ *                                its consumer; then positive-pair term and Jacobian of F.normalize
  * (the image side uses jsd_dense_backward_image_side with V_all = v_all[parity][rank]).
  * Buffers come from jsd_peer_alloc (cudaMalloc, zero-filled) and are mapped into the other processes with
  * jsd_peer_export / jsd_peer_open (CUDA IPC).  The gathered V buffer is double-buffered by the step's parity
@@ -176,7 +178,7 @@ typedef struct jsd_peer_ctx {
   int64_t rows;                          /* rows per rank (the same on every rank) */
   int64_t dim;                           /* D */
   void* v_all[2][JSD_MAX_PEERS];         /* [parity][q]: rank q's gathered V [world * rows, D] bf16, as mapped here */
-  void* stage[JSD_MAX_PEERS];            /* rank q's staging [world, rows, D] fp32 */
+  void* stage[JSD_MAX_PEERS];            /* rank q's dV partial [world * rows, D] fp32, as mapped here */
   int32_t* flags[JSD_MAX_PEERS];         /* rank q's flag block, zero before the first step */
 } jsd_peer_ctx;
 

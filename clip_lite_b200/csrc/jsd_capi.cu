@@ -230,6 +230,38 @@ int launch_normalize_bwd(const jsd::NormBwdJob& job, int count, int64_t rows, in
   return 0;
 }
 
+// One non-blocking helper stream and two events per device: the image-side Jacobian kernel (HBM-bound) runs on it
+// next to the dV contraction, whose ragged last wave leaves 40 SMs idle for half of its run time.  Fork / join by
+// events, so the pattern is legal inside a CUDA-graph capture of the caller's stream.  JSD_OVERLAP=0 disables it.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("JSD_OVERLAP");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (s.stream == nullptr) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    (void)cap;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      s = SideStream{};
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 // the second int of the forward workspace's 16-byte ticket area serialises the dL/dt reduction
 int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; }
 
@@ -476,7 +508,23 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
                        void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
   JSD_REQUIRE(F && G && U && V && inv_f && inv_g && gdiag && dF && dG, "jsd_dense_backward: null pointer argument");
   JSD_REQUIRE(dt_out && acc_u && acc_v && rowdot && workspace, "jsd_dense_backward: null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
   if (int rc = jsd_dense_bwd_du(Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
+  SideStream* side = side_stream();
+  if (side != nullptr) {
+    // image-side Jacobian (+ gamma * dL/dt) on the helper stream, next to the dV contraction.  The contraction
+    // is enqueued FIRST so that its persistent CTAs take the SMs and the Jacobian's blocks fill in as they retire.
+    JSD_CUDA_OK(cudaEventRecord(side->fork, st));
+    if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
+    JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if (int rc = jsd_normalize_bwd(F, dtype, B, D, inv_f, acc_u, V, 0, gdiag, t_dev, gamma_dev, B, dF, rowdot,
+                                   workspace, dt_out, side->stream))
+      return rc;
+    JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+    return jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, nullptr,
+                             nullptr, stream);
+  }
   if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
   // both Jacobians (image side = job 0, text side = job 1) and gamma * dL/dt = sum_i <u_i, dU_i> in one launch
   jsd::NormBwdJob job{};
@@ -493,7 +541,6 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
   job.rowdot = rowdot;
   job.ticket = dt_ticket(workspace);
   job.dt_out = dt_out;
-  cudaStream_t st = (cudaStream_t)stream;
   const float inv_rows = (float)(1.0 / (double)B);
   JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 2, B, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
 }
@@ -639,6 +686,31 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
   const float inv_rows = (float)(1.0 / (double)ctx->rows);
   JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 1, ctx->rows, ctx->dim, gdiag, t_dev, gamma_dev, inv_rows,
                                                      st)));
+}
+
+int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
+                            const void* U, const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg,
+                            const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
+                            float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
+  if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_backward")) return rc;
+  JSD_REQUIRE(parity == 0 || parity == 1, "jsd_peer_dense_backward: parity must be 0 or 1");
+  const void* V_all = ctx->v_all[parity][ctx->rank];
+  const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim, off = ctx->rows * ctx->rank;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = jsd_dense_bwd_du(Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
+  SideStream* side = side_stream();
+  cudaStream_t js = side ? side->stream : st;       // image-side Jacobian next to the dV contraction (enqueued first)
+  if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
+  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, stream)) return rc;
+  if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  if (int rc = jsd_normalize_bwd(F, dtype, M, D, inv_f, acc_u, V_all, off, gdiag, t_dev, gamma_dev, M, dF, rowdot,
+                                 workspace, dt_out, js))
+    return rc;
+  if (side) {
+    JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+  }
+  return jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, dG, stream);
 }
 
 int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,

@@ -132,6 +132,20 @@ class PeerExchange:
         _lib.call("jsd_peer_dense_bwd_dv", gmat.data_ptr(), gmat.shape[1], u.data_ptr(), self._ctx_ptr,
                   tt.data_ptr(), gg.data_ptr(), K._stream())
 
+    def dense_backward(self, f, g, t, gamma, parity: int, u, inv_f, inv_g, gmat, gdiag):
+        """Whole backward of a step in one library call.  Returns (dF, dG, dt)."""
+        m, d = f.shape
+        tt, gg = K._scalar(t, "temperature"), K._scalar(gamma, "gamma")
+        acc = torch.empty(m, d, dtype=torch.float32, device=f.device)
+        small = torch.empty(m + 1, dtype=torch.float32, device=f.device)
+        df, dg = torch.empty_like(f), torch.empty_like(g)
+        ws = K.dense_workspace(f.device)
+        _lib.call("jsd_peer_dense_backward", f.data_ptr(), g.data_ptr(), K._code(f), self._ctx_ptr, parity,
+                  u.data_ptr(), inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
+                  tt.data_ptr(), gg.data_ptr(), acc.data_ptr(), small.data_ptr(), ws.data_ptr(), df.data_ptr(),
+                  dg.data_ptr(), small[m:].data_ptr(), K._stream())
+        return df, dg, small[m]
+
     def normalize_bwd_text(self, g: torch.Tensor, inv_g, u, gdiag, t, gamma) -> torch.Tensor:
         tt, gg = K._scalar(t, "temperature"), K._scalar(gamma, "gamma")
         dg = torch.empty_like(g)
@@ -180,12 +194,7 @@ class _PeerDenseFn(torch.autograd.Function):
         fc, gc, t, u, inv_f, inv_g, gmat, gdiag = ctx.saved_tensors
         with torch.autocast(fc.device.type, enabled=False):
             gamma = grad_loss.float()
-            v_all = ex.v_all[ctx.parity]
-            # text-side partial first: its flag goes out early and the peers' partials arrive while the
-            # image side computes (the gathered V is double-buffered, so the order is free)
-            ex.dense_bwd_dv(gmat, u, t, gamma)
-            df, dt = K.dense_backward_image_side(fc, v_all, inv_f, gmat, gdiag, t, gamma, ex.rank * ex.rows)
-            dg = ex.normalize_bwd_text(gc, inv_g, u, gdiag, t, gamma)
+            df, dg, dt = ex.dense_backward(fc, gc, t, gamma, ctx.parity, u, inv_f, inv_g, gmat, gdiag)
         fd, gd, td = ctx.dtypes
         return df.to(fd), dg.to(gd), dt.to(td), None
 
@@ -213,10 +222,7 @@ class PeerGraphedStep:
         def step(parity):
             u, inv_f, inv_g = ex.normalize_push(self.f, self.g, parity)
             out4, loss, gmat, gdiag = ex.dense_fwd(u, self.t, parity)
-            ex.dense_bwd_dv(gmat, u, self.t, self.gamma)
-            df, dt = K.dense_backward_image_side(self.f, ex.v_all[parity], inv_f, gmat, gdiag, self.t, self.gamma,
-                                                 ex.rank * ex.rows)
-            dg = ex.normalize_bwd_text(self.g, inv_g, u, gdiag, self.t, self.gamma)
+            df, dg, dt = ex.dense_backward(self.f, self.g, self.t, self.gamma, parity, u, inv_f, inv_g, gmat, gdiag)
             return loss, df, dg, dt
 
         p0 = ex.step & 1                   # pushes below come in (p0, p0 ^ 1) pairs: the exchange's parity is kept

@@ -122,7 +122,9 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
 /* Single-GPU convenience (M == N == B, row_offset 0): the whole forward, resp. the whole backward, in
  * one call, so that the host pays one FFI crossing per autograd direction (2 + 3 kernel launches per step).
  *   forward : jsd_normalize_cast_pair(F, G), jsd_dense_fwd (loss reduced by its last CTA)
- *   backward: jsd_dense_bwd_du, jsd_dense_bwd_dv, ONE launch for both jsd_normalize_bwd's and dt_out
+ *   backward: jsd_dense_bwd_du, then the image-side jsd_normalize_bwd (+ dt_out) on a library-owned helper
+ *             stream next to jsd_dense_bwd_dv (forked / joined with events: legal under CUDA-graph capture), then
+ *             the text-side jsd_normalize_bwd; with JSD_OVERLAP=0: both Jacobians in one launch after the GEMMs
  * F, G [B, D] in `dtype`; U, V bf16 [B, D]; acc_u, acc_v fp32 [B, D] and rowdot fp32 [B] scratch;
  * workspace = the forward's; dF, dG in `dtype`; dt_out = gamma * dL/dt. */
 int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U_bf16,
@@ -197,6 +199,14 @@ int jsd_peer_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16
 int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g,
                                 const void* U_bf16, const float* gdiag, const float* t_dev, const float* gamma_dev,
                                 void* dG, jsd_stream_t stream);
+
+/* Whole backward of a peer-exchange step in one call: dU contraction, then the image-side Jacobian (+ dt_out =
+ * gamma * dL_r/dt) on a helper stream NEXT TO the dV contraction (whose ragged last wave leaves SMs idle), then the
+ * text-side Jacobian (pull).  acc_u fp32 [rows, D] and rowdot fp32 [rows] are scratch; workspace = the forward's. */
+int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
+                            const void* U_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16,
+                            int64_t ldg, const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
+                            float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or

@@ -371,6 +371,35 @@ def run_b200(args, wl):
             for _ in range(3):
                 fn()
             stage_ms[name] = timed(fn, n_meas) / n_meas
+    # ---- N > 1: the same row slab with pre-gathered operands and NO exchange (the numerator of
+    # the weak-scaling efficiency E(R) = t_slab_nocomm / t_step); replayed from a CUDA graph like the step itself
+    slab_nocomm_ms = None
+    if world > 1:
+        f_c, g_c = f_dev.detach(), g_dev.detach()
+
+        def local_slab():
+            uu, vv, i_f, i_g = K.normalize_cast_pair(f_c, g_c)
+            _, _, gm, gd = K.dense_fwd(uu, v_all, t_c, row_offset=rank * rows)
+            dv_part = K.dense_bwd_dv(gm, uu, batch, t_c, gamma)
+            K.dense_backward_image_side(f_c, v_all, i_f, gm, gd, t_c, gamma, rank * rows)
+            K.normalize_bwd(g_c, i_g, dv_part[rank * rows:(rank + 1) * rows], uu, 0, gd, t_c, gamma, rows)
+
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                local_slab()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr), torch.no_grad():
+                local_slab()
+            for _ in range(3):
+                gr.replay()
+            slab_nocomm_ms = timed(gr.replay, n_meas) / n_meas
+        except Exception as exc:
+            print(f"[bench] slab-without-exchange timing failed ({type(exc).__name__}: {exc})", file=sys.stderr)
+            torch.cuda.synchronize()
     flops_per_launch = 2.0 * rows * batch * dim                       # S = U V^T, dU = G V, dV = G^T U
     gemm_ms = sum(stage_ms.values())
     achieved = 3 * flops_per_launch / (gemm_ms * 1e-3) / 1e12
@@ -409,6 +438,10 @@ def run_b200(args, wl):
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
             "tflops_6B2D": 6.0 * rows * batch * dim / (ms_per_step * 1e-3) / 1e12,
         }
+        if slab_nocomm_ms is not None:
+            line["slab_nocomm"] = {"ms_per_step": slab_nocomm_ms,
+                                   "note": "this rank's row slab with pre-gathered text rows and no exchange, same "
+                                           "kernels, graph replay (SURVEY 8d: E(R) = t_slab_nocomm / t_step)"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -9,6 +9,7 @@
 
 #include "jsd_dense.cuh"
 #include "jsd_rowwise.cuh"
+#include "jsd_score.cuh"
 
 #ifndef JSD_L2_PROMO
 #define JSD_L2_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
@@ -711,6 +712,91 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
     JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
   }
   return jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, dG, stream);
+}
+
+/* ------------------------------------------------------------------ retrieval / zero-shot scoring */
+int jsd_split_bf16x3(const void* X, int dtype, int64_t rows, int64_t D, int side, int normalize, void* out,
+                     jsd_stream_t stream) {
+  JSD_REQUIRE(X && out && (side == 0 || side == 1), "jsd_split_bf16x3: bad argument");
+  JSD_REQUIRE(fits_int(rows) && fits_int(3 * D), "jsd_split_bf16x3: bad shape");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case JSD_F32:
+      jsd::split_bf16x3_kernel<float><<<grid, 256, 0, st>>>((const float*)X, (int)rows, (int)D, side, normalize,
+                                                           (__nv_bfloat16*)out);
+      break;
+    case JSD_BF16:
+      jsd::split_bf16x3_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)X, (int)rows, (int)D, side,
+                                                                   normalize, (__nv_bfloat16*)out);
+      break;
+    case JSD_F16:
+      jsd::split_bf16x3_kernel<__half><<<grid, 256, 0, st>>>((const __half*)X, (int)rows, (int)D, side, normalize,
+                                                            (__nv_bfloat16*)out);
+      break;
+    default: return fail("unsupported dtype code %d", dtype);
+  }
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int score_launch(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const jsd::GemmParams& proto,
+                        cudaStream_t st) {
+  const int cg = pick_cta_group(M);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap(&tmA, A, K, M, K, jsd::BLOCK_K, jsd::BLOCK_M)) return rc;
+  if (int rc = make_tmap(&tmB, B, K, N, K, jsd::BLOCK_K, jsd::b_rows_per_cta(cg))) return rc;
+  jsd::GemmParams p = proto;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.n_fastest = 0;
+  return cg == 2 ? launch_gemm<jsd::MODE_SCORE, false, false, 2>(tmA, tmB, p, nullptr, st)
+                 : launch_gemm<jsd::MODE_SCORE, false, false, 1>(tmA, tmB, p, nullptr, st);
+}
+
+int jsd_score_ranks(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const int32_t* row_tgt_ptr,
+                    const int32_t* row_tgt_idx, const int32_t* col_tgt, void* thr_row_scratch, float* thr_col_scratch,
+                    int32_t* rank_row, int32_t* rank_col, jsd_stream_t stream) {
+  JSD_REQUIRE(A && B, "jsd_score_ranks: null pointer argument");
+  JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(K) && K % 8 == 0, "jsd_score_ranks: bad shape (K %% 8 == 0)");
+  const bool rows = row_tgt_ptr != nullptr, cols = col_tgt != nullptr;
+  JSD_REQUIRE(rows || cols, "jsd_score_ranks: neither row nor column targets given");
+  JSD_REQUIRE(!rows || (row_tgt_idx && thr_row_scratch && rank_row), "jsd_score_ranks: row side incomplete");
+  JSD_REQUIRE(!cols || (thr_col_scratch && rank_col), "jsd_score_ranks: column side incomplete");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows) {
+    JSD_CUDA_OK(cudaMemsetAsync(thr_row_scratch, 0, (size_t)M * 4, st));        // encoding 0 = no target
+    JSD_CUDA_OK(cudaMemsetAsync(rank_row, 0, (size_t)M * 4, st));
+  }
+  if (cols) {
+    JSD_CUDA_OK(cudaMemsetAsync(thr_col_scratch, 0x7f, (size_t)N * 4, st));     // 3.4e38: nothing beats "no target"
+    JSD_CUDA_OK(cudaMemsetAsync(rank_col, 0, (size_t)N * 4, st));
+  }
+  jsd::GemmParams p{};
+  p.row_tgt_ptr = rows ? row_tgt_ptr : nullptr;
+  p.row_tgt_idx = row_tgt_idx;
+  p.col_tgt = col_tgt;
+  p.thr_row_enc = rows ? (unsigned*)thr_row_scratch : nullptr;
+  p.thr_col = cols ? thr_col_scratch : nullptr;
+  p.cnt_row = rank_row;
+  p.cnt_col = rank_col;
+  p.score_pass = 0;                 // pass 0: the target scores, taken from the very tiles pass 1 will recompute
+  if (int rc = score_launch(A, B, M, N, K, p, st)) return rc;
+  p.score_pass = 1;                 // pass 1: count the entries that beat them
+  return score_launch(A, B, M, N, K, p, st);
+}
+
+int jsd_score_argmax(const void* A, const void* B, int64_t M, int64_t N, int64_t K, unsigned long long* best,
+                     jsd_stream_t stream) {
+  JSD_REQUIRE(A && B && best, "jsd_score_argmax: null pointer argument");
+  JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(K) && K % 8 == 0, "jsd_score_argmax: bad shape (K %% 8 == 0)");
+  cudaStream_t st = (cudaStream_t)stream;
+  JSD_CUDA_OK(cudaMemsetAsync(best, 0, (size_t)M * 8, st));
+  jsd::GemmParams p{};
+  p.best = best;
+  p.score_pass = 1;
+  return score_launch(A, B, M, N, K, p, st);
 }
 
 int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, int64_t M,

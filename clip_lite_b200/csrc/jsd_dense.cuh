@@ -78,7 +78,7 @@ __host__ __device__ constexpr int gemm_smem_bytes(int cg, int mode) {
          256 /* barriers */;
 }
 
-enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1 };
+enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1, MODE_SCORE = 2 };   // SCORE shares GRAD's pipeline shape
 
 struct GemmParams {
   alignas(64) CUtensorMap tmG;   // FWD: Gmat [M, N] bf16 as the target of the epilogue's TMA stores (box 64 x 32)
@@ -107,6 +107,18 @@ struct GemmParams {
   int stream_k;
   int* sk_flags;
   float* sk_slots;
+  // SCORE (retrieval / zero-shot scoring, S = A B^T never stored).  Pass 0 extracts the target scores, pass 1
+  // counts the entries that beat them -- the same tiles, the same accumulation order, so a target never beats
+  // itself and no tie margin is needed.
+  int score_pass;
+  const int* row_tgt_ptr;        // CSR of each row's target columns (may be null)
+  const int* row_tgt_idx;
+  const int* col_tgt;            // [N] target row of each column, -1 = none (may be null)
+  unsigned* thr_row_enc;         // [M] max target score per row, order-preserving encoding (0 = no target)
+  float* thr_col;                // [N] target score per column
+  int* cnt_row;                  // [M] += #{j : S_ij > thr_row[i]}
+  int* cnt_col;                  // [N] += #{i : S_ij > thr_col[j]}
+  unsigned long long* best;      // [M] max over j of (enc(S_ij) << 32 | ~j): row maximum, smallest column on ties
   // peer-memory exchange (multi-GPU).  wait_*: the TMA producer holds its first load until every rank's flag has
   // reached *wait_counter (the gathered B operand was written by peer GPUs).  peer_*: the output of a GRAD launch
   // is read by the other ranks straight out of this GPU's memory; the last CTA of the launch bumps *peer_counter
@@ -134,6 +146,15 @@ __device__ __forceinline__ void neg_terms(float s, float tau_l2, float& d, float
   d = 1.f + e;
   const float rr = rcp_approx(d);
   sg = s >= 0.f ? rr : 1.f - rr;
+}
+
+// Order-preserving map float -> unsigned (so that atomicMax on the encoding is a float max); 0 is below every float.
+__device__ __forceinline__ unsigned enc_ordered(float f) {
+  const unsigned b = __float_as_uint(f);
+  return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e ^ 0x80000000u) : ~e);
 }
 
 // Work iterator shared by the three roles: yields (tile, k_begin, k_end) segments.
@@ -447,11 +468,70 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BLOCK_N + cgrp * COLS_PER_WARP + ((uint32_t)(32 * q) << 16);
 
+      // SCORE: per-row state of this tile (thread = row)
+      [[maybe_unused]] int sc_cnt = 0, sc_tb = 0, sc_te = 0, sc_bj = 0;
+      [[maybe_unused]] float sc_thr = 0.f, sc_bv = 0.f;
+      [[maybe_unused]] bool sc_has_best = false;
+      if constexpr (MODE == MODE_SCORE) {
+        if (row_ok) {
+          if (p.score_pass == 0 && p.row_tgt_ptr != nullptr) {
+            sc_tb = p.row_tgt_ptr[grow];
+            sc_te = p.row_tgt_ptr[grow + 1];
+          }
+          if (p.score_pass == 1 && p.thr_row_enc != nullptr) sc_thr = dec_ordered(p.thr_row_enc[grow]);
+        }
+      }
+
       // One 32-row x CW-column chunk held in registers (thread = row, v[j] = column col0 + j).
       auto process_chunk = [&](uint32_t(&v)[CW], const int c) {
         const int col_in_tile = cgrp * COLS_PER_WARP + CW * c;
         const int col0 = n0 + col_in_tile;
-        if constexpr (MODE == MODE_FWD) {
+        if constexpr (MODE == MODE_SCORE) {
+          const int ncols = min(CW, p.N - col0);            // existing columns of this chunk (may be <= 0)
+          const int nvalid = row_ok ? ncols : 0;            // ... that this thread's row may look at
+          if (p.score_pass == 0) {
+            for (int k = sc_tb; k < sc_te; ++k) {
+              const int tc = p.row_tgt_idx[k] - col0;
+              if ((unsigned)tc < (unsigned)max(nvalid, 0)) {
+                float val = 0.f;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) val = (j == tc) ? __uint_as_float(v[j]) : val;
+                atomicMax(p.thr_row_enc + grow, enc_ordered(val));
+              }
+            }
+            if (p.col_tgt != nullptr) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if (j < nvalid && p.col_tgt[col0 + j] == grow) p.thr_col[col0 + j] = __uint_as_float(v[j]);
+            }
+          } else {
+            if (p.thr_row_enc != nullptr) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) sc_cnt += (j < nvalid && __uint_as_float(v[j]) > sc_thr) ? 1 : 0;
+            }
+            if (p.thr_col != nullptr) {
+              int mine = 0;
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const bool g = j < nvalid && __uint_as_float(v[j]) > p.thr_col[col0 + j];
+                const unsigned b = __ballot_sync(0xffffffffu, g);
+                if (lane == j) mine = __popc(b);
+              }
+              if (lane < ncols && mine > 0) atomicAdd(p.cnt_col + col0 + lane, mine);
+            }
+            if (p.best != nullptr) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const float sv = __uint_as_float(v[j]);
+                if (j < nvalid && (!sc_has_best || sv > sc_bv)) {
+                  sc_bv = sv;
+                  sc_bj = col0 + j;
+                  sc_has_best = true;
+                }
+              }
+            }
+          }
+        } else if constexpr (MODE == MODE_FWD) {
           // ---- scores -> softplus / sigmoid.  Every element first takes the negative-pair path;
           //      the (rare) chunk holding this warp's positives is corrected afterwards.
           if ((col0 + CW > p.N) || (m0 + BLOCK_M > p.M)) {
@@ -593,6 +673,13 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_store_2d(&p.tmG, g_stage, n0 + cgrp * COLS_PER_WARP, m0 + 32 * q);
             tma_store_commit();
           }
+        }
+      }
+      if constexpr (MODE == MODE_SCORE) {
+        if (row_ok && p.score_pass == 1) {
+          if (sc_cnt > 0) atomicAdd(p.cnt_row + grow, sc_cnt);
+          if (sc_has_best)
+            atomicMax(p.best + grow, ((unsigned long long)enc_ordered(sc_bv) << 32) | (0xFFFFFFFFu - (unsigned)sc_bj));
         }
       }
       if constexpr (MODE == MODE_GRAD) {

@@ -208,6 +208,29 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
                             int64_t ldg, const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
                             float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
+/* ------------------------------------------------------------------ retrieval / zero-shot scoring
+ * replaces: retrieval.py:143 (`sims_matrix = image_embeds @ text_embeds.t()`, copied to the host) + the NumPy
+ * argsort loops of itm_eval (retrieval.py:163-187), and zero_shot.py:155 (`torch.max(features @ prompts.t(), 1)`).
+ * S = A B^T runs on the tensor-core kernel and is never stored.
+ *
+ * jsd_split_bf16x3: fp32-faithful scores from bf16 tensor cores.  out [rows, 3 D] bf16 = (hi, hi, lo) for side 0 and
+ *   (hi, lo, hi) for side 1, hi = bf16(x), lo = bf16(x - hi); then <A'_i, B'_j> = <a,b> up to ~2^-17.  normalize != 0
+ *   first scales each row to unit L2 norm (F.normalize).  Use the outputs as A / B below with K = 3 D.
+ * jsd_score_ranks: rank_row[i] = #{j : S_ij > max_{t in targets(i)} S_it}  (image -> text rank of the best ground
+ *   truth: CSR row_tgt_ptr [M+1] / row_tgt_idx), rank_col[j] = #{i : S_ij > S_{col_tgt[j], j}} (text -> image;
+ *   col_tgt [N], -1 = none).  Either side may be omitted (NULL).  Two passes over the same tiles: the first extracts
+ *   the target scores, the second counts, so a target is compared with bit-identical arithmetic (no tie margin).
+ *   thr_row_scratch [M] / thr_col_scratch [N]: 4-byte scratch per row / column.
+ * jsd_score_argmax: best[i] = max_j ((ordered bits of S_ij) << 32 | (0xFFFFFFFF - j)): the row maximum and, on
+ *   ties, the smallest column; column = 0xFFFFFFFF - (best & 0xFFFFFFFF). */
+int jsd_split_bf16x3(const void* X, int dtype, int64_t rows, int64_t D, int side, int normalize, void* out_bf16,
+                     jsd_stream_t stream);
+int jsd_score_ranks(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, const int32_t* row_tgt_ptr,
+                    const int32_t* row_tgt_idx, const int32_t* col_tgt, void* thr_row_scratch, float* thr_col_scratch,
+                    int32_t* rank_row, int32_t* rank_col, jsd_stream_t stream);
+int jsd_score_argmax(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, unsigned long long* best,
+                     jsd_stream_t stream);
+
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or
  * B^T [K, ldb] (b_mn_major = 1).  sk_workspace as above (NULL => whole tiles only).

@@ -251,8 +251,6 @@ SideStream* side_stream() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& s = per_dev[dev];
   if (s.stream == nullptr) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    (void)cap;
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {

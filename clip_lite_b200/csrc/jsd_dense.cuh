@@ -141,11 +141,36 @@ constexpr float kMaskedScore = -30000.f;
 // softplus(x) = max(x, 0) + log(d) is NOT formed per element: the epilogue accumulates sum max(s, 0)
 // (scaled by tau once, in the finalize kernel) and the PRODUCT of the d's of a chunk (each in [1, 2], so
 // 16 of them cannot overflow), and takes one MUFU.LG2 per chunk: log-sum = log-product.
+//
+// The epilogue is bound by the XU (MUFU) pipe, not by instruction issue (ncu: XU is the busiest non-tensor pipe,
+// warps stall in mio_throttle), so 1/d does NOT go through MUFU.RCP: d lies in [1, 2], a minimax cubic gives
+// 1/d to 1.7e-3 and one Newton step squares that to 3e-6 -- five FMA-pipe instructions, far below the bf16
+// rounding (2e-3) of the only consumer, Gmat.  sigma(x < 0) = e / d is formed as e * (1/d): no cancellation.
+#ifndef JSD_FWD_PACKED_F32X2
+#define JSD_FWD_PACKED_F32X2 1
+#endif
+#ifndef JSD_FWD_RCP_POLY
+#define JSD_FWD_RCP_POLY 0
+#endif
+__device__ __forceinline__ float rcp_1to2(float d) {
+#if JSD_FWD_RCP_POLY
+  float r = fmaf(d, -0.22183725f, 1.33102348f);
+  r = fmaf(d, r, -2.93934318f);
+  r = fmaf(d, r, 2.82842386f);
+  return r * fmaf(-d, r, 2.f);
+#else
+  return rcp_approx(d);
+#endif
+}
 __device__ __forceinline__ void neg_terms(float s, float tau_l2, float& d, float& sg) {
   const float e = ex2_approx(-fabsf(s * tau_l2));
   d = 1.f + e;
-  const float rr = rcp_approx(d);
+  const float rr = rcp_1to2(d);
+#if JSD_FWD_RCP_POLY
+  sg = s >= 0.f ? rr : e * rr;
+#else
   sg = s >= 0.f ? rr : 1.f - rr;
+#endif
 }
 
 // Order-preserving map float -> unsigned (so that atomicMax on the encoding is a float max); 0 is below every float.
@@ -543,6 +568,25 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (j >= nvalid) v[j] = __float_as_uint(kMaskedScore);
           }
           uint32_t packed[CW / 2];
+#if JSD_FWD_PACKED_F32X2
+          // two elements per FMA-pipe instruction (sm_100 f32x2 arithmetic): the epilogue's ALU work runs just as
+          // long as the MMAs of a tile, so every instruction saved here comes off the kernel time
+          float2 dprod2 = make_float2(1.f, 1.f), relu2 = make_float2(0.f, 0.f);
+          const float2 tl2 = make_float2(tau_l2, tau_l2), one2 = make_float2(1.f, 1.f), mone2 = make_float2(-1.f, -1.f);
+#pragma unroll
+          for (int j = 0; j < CW; j += 2) {
+            const float2 sv = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            const float2 y = __fmul2_rn(sv, tl2);
+            const float2 d = __fadd2_rn(make_float2(ex2_approx(-fabsf(y.x)), ex2_approx(-fabsf(y.y))), one2);
+            const float2 rr = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+            const float2 om = __ffma2_rn(rr, mone2, one2);                      // 1 - rr
+            dprod2 = __fmul2_rn(dprod2, d);
+            relu2 = __fadd2_rn(relu2, make_float2(fmaxf(sv.x, 0.f), fmaxf(sv.y, 0.f)));
+            packed[j >> 1] = pack_bf16x2(sv.x >= 0.f ? rr.x : om.x, sv.y >= 0.f ? rr.y : om.y);
+          }
+          relu_sum += relu2.x + relu2.y;
+          lg_sum += lg2_approx(dprod2.x * dprod2.y);      // 16 factors in [1, 2]: no overflow
+#else
           float dprod = 1.f;
 #pragma unroll
           for (int j = 0; j < CW; j += 2) {
@@ -558,6 +602,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             packed[j >> 1] = pack_bf16x2(sg[0], sg[1]);
           }
           lg_sum += lg2_approx(dprod);
+#endif
           const int dj = p.row_offset + grow - col0;          // this row's positive sits at v[dj] if 0 <= dj < CW
           if (__any_sync(0xffffffffu, row_ok && (unsigned)dj < (unsigned)CW)) {
             float s_d = 0.f;

@@ -147,9 +147,13 @@ class JSDInfoMaxLoss(nn.Module):
       neg_mode  "shift1": one negative per row, the text batch rolled by one
                 (reference semantics, HBM-bound fused kernel);
                 "dense": every off-diagonal pair is a negative (tensor-core kernels).
-      gather    with neg_mode="dense": all-gather the text embeddings over
-                ``process_group`` so that each rank scores its rows against the
-                global batch (gradients of the text side are reduce-scattered back).
+      gather    with neg_mode="dense": each rank scores its rows against the text
+                embeddings of every rank of ``process_group`` (gradients of the text
+                side are summed back on the owning rank).
+      exchange  how ``gather`` moves the data: "nccl" (default: all-gather + reduce-
+                scatter collectives, any process group) or "peer" (both exchanges fused
+                into the kernels over NVLink peer memory; <= 8 GPUs of one node, fixed
+                per-rank batch size -- see clip_lite_b200.peer).
     """
 
     def __init__(
@@ -166,6 +170,7 @@ class JSDInfoMaxLoss(nn.Module):
         neg_mode: str = "shift1",
         gather: bool = False,
         process_group=None,
+        exchange: str = "nccl",
     ):
         super().__init__()
         if type not in _DOT_TYPES + _CONCAT_TYPES:
@@ -174,6 +179,8 @@ class JSDInfoMaxLoss(nn.Module):
             raise ValueError(f"neg_mode must be 'shift1' or 'dense', got {neg_mode!r}")
         if gather and neg_mode != "dense":
             raise ValueError("gather=True requires neg_mode='dense'")
+        if exchange not in ("nccl", "peer"):
+            raise ValueError(f"exchange must be 'nccl' or 'peer', got {exchange!r}")
         if neg_mode == "dense" and type not in _DOT_TYPES:
             raise ValueError("neg_mode='dense' needs the dot critic (type='dot' or 'dotcon')")
         self.prior_weight = prior_weight
@@ -182,6 +189,7 @@ class JSDInfoMaxLoss(nn.Module):
         self.neg_mode = neg_mode
         self.gather = gather
         self.process_group = process_group
+        self.exchange = exchange
 
         self.global_d = (GlobalDiscriminatorDot(image_sz=image_dim, text_sz=text_dim) if type in _DOT_TYPES
                          else GlobalDiscriminator(sz=image_dim + text_dim))
@@ -225,7 +233,10 @@ class JSDInfoMaxLoss(nn.Module):
             f = _forward_block_twice(critic.img_block, feats1)
             g = _forward_block_twice(critic.text_block, feats2)
             if allow_dense and self.neg_mode == "dense":
-                if self.gather:
+                if self.gather and self.exchange == "peer":
+                    from . import peer
+                    loss, _ = peer.peer_dense_loss(f, g, critic.temperature, self.process_group)
+                elif self.gather:
                     from . import parallel
                     loss, _ = parallel.gathered_dense_loss(f, g, critic.temperature, self.process_group)
                 else:

@@ -32,12 +32,12 @@ SIGNATURES = {
                                   c_void_p]),
     "jsd_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_cast_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "jsd_dense_backward_image_side": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                               c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_streamk_workspace_bytes": (c_size_t, []),
     "jsd_streamk_flag_bytes": (c_size_t, []),
     "jsd_dense_bwd_du": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
@@ -57,12 +57,13 @@ SIGNATURES = {
                                         c_void_p]),
     "jsd_peer_dense_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
-    "jsd_peer_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_peer_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "jsd_peer_normalize_bwd_text": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p]),
     "jsd_peer_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_split_bf16x3": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "jsd_score_ranks": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -82,7 +83,7 @@ class PeerCtx(ctypes.Structure):
                 ("flags", c_void_p * MAX_PEERS)]
 
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 

@@ -113,9 +113,18 @@ int pick_cta_group(int64_t m_rows) {
   return m_rows > jsd::BLOCK_M ? 2 : 1;
 }
 
+// Stream-K policies of the GRAD launches (a workspace must be given for any of them):
+//   0               never (the product's fused backward entry points: they use plan_split() instead, measured
+//                   3x faster on underfilled launches -- stream-K's hand-off costs ~30 us there);
+//   SK_UNDERFILLED  cut tiles when they fill at most half of the workers;
+//   SK_RAGGED       additionally balance a ragged last wave (1.73 waves at B = 8192, D = 1024).  Implemented and
+//                   tested, but measured 2-5 % slower than whole tiles on the power-capped B200,
+//                   so only the explicit GEMM entry points ask for it.
+enum SkPolicy { SK_UNDERFILLED = 1, SK_RAGGED = 2 };
+
 template <int MODE, bool A_MN, bool B_MN, int CG>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams p, void* sk_workspace,
-                cudaStream_t st, int* grid_out = nullptr) {
+                cudaStream_t st, int sk_policy = SK_RAGGED) {
   auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN, CG>;
   constexpr int smem = jsd::gemm_smem_bytes(CG, MODE);
   static bool configured = false;
@@ -128,25 +137,32 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
   const int max_workers = sms / CG;                         // a worker = one CTA or one CTA pair
   const int n_blocks = (p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N;
   const long long tiles = (long long)((p.M + jsd::BLOCK_M * CG - 1) / (jsd::BLOCK_M * CG)) * n_blocks;
-  int workers = (int)(tiles < max_workers ? tiles : max_workers);
-  // stream-K (opt-in: the caller passes a workspace) balances a ragged last wave, e.g. 128 pair tiles on 74 pairs
+  const long long work_items = tiles * (MODE == jsd::MODE_GRAD && p.ksplit > 1 ? p.ksplit : 1);   // split-K slices
+  int workers = (int)(work_items < max_workers ? work_items : max_workers);
+  // stream-K (opt-in: the caller passes a workspace), see SkPolicy
   p.stream_k = 0;
   const int sk_workers = max_workers / n_blocks * n_blocks;   // whole groups of n_blocks workers
-  const long long m_blocks = tiles / n_blocks;
-  if (MODE == jsd::MODE_GRAD && sk_workspace != nullptr && p.n_fastest && sk_workers >= n_blocks &&
-      m_blocks % (sk_workers / n_blocks) != 0 && tiles > sk_workers && sk_workers * 16 >= max_workers * 15 &&
-      sk_workers * CG <= jsd::SK_MAX_CTAS &&
-      // every group must receive at least one k-chunk of the stream-K m-blocks (no empty ranges)
-      (m_blocks % (sk_workers / n_blocks)) *
-              ((p.K + jsd::BLOCK_K * jsd::k_atoms(MODE) - 1) / (jsd::BLOCK_K * jsd::k_atoms(MODE))) >=
-          sk_workers / n_blocks) {
-    p.stream_k = 1;
-    p.sk_flags = reinterpret_cast<int*>(sk_workspace);
-    p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
-    workers = sk_workers;
+  static int sk_enabled = -1;                                  // development knob: JSD_STREAMK=0 disables it
+  if (sk_enabled < 0) {
+    const char* e = getenv("JSD_STREAMK");
+    sk_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (MODE == jsd::MODE_GRAD && sk_enabled && sk_workspace != nullptr && p.n_fastest && sk_workers >= n_blocks) {
+    const long long m_blocks = tiles / n_blocks;
+    const int groups = sk_workers / n_blocks;
+    const long long sk_mb = m_blocks % groups;                 // m-blocks that are cut along the contraction
+    const long long nk = (p.K + jsd::BLOCK_K * jsd::k_atoms(MODE) - 1) / (jsd::BLOCK_K * jsd::k_atoms(MODE));
+    const bool underfilled = sk_policy >= SK_UNDERFILLED && tiles * 2 <= sk_workers;
+    const bool ragged = sk_policy >= SK_RAGGED && tiles > sk_workers && sk_mb != 0;
+    if ((underfilled || ragged) && sk_workers * 16 >= max_workers * 15 && sk_workers * CG <= jsd::SK_MAX_CTAS &&
+        sk_mb * nk >= groups) {                                // every group receives at least one k-chunk
+      p.stream_k = 1;
+      p.sk_flags = reinterpret_cast<int*>(sk_workspace);
+      p.sk_slots = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
+      workers = sk_workers;
+    }
   }
   const int grid = workers * CG;
-  if (grid_out) *grid_out = grid;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(jsd::GEMM_THREADS);
@@ -165,9 +181,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
 
 template <int MODE>
 int launch_gemm_any(bool a_mn, bool b_mn, int cg, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                    const jsd::GemmParams& p, void* sk_workspace, cudaStream_t st) {
+                    const jsd::GemmParams& p, void* sk_workspace, cudaStream_t st, int sk_policy = SK_RAGGED) {
 #define JSD_GEMM_CASE(A, B, C) \
-  if (a_mn == A && b_mn == B && cg == C) return launch_gemm<MODE, A, B, C>(tmA, tmB, p, sk_workspace, st);
+  if (a_mn == A && b_mn == B && cg == C) return launch_gemm<MODE, A, B, C>(tmA, tmB, p, sk_workspace, st, sk_policy);
   JSD_GEMM_CASE(false, false, 1) JSD_GEMM_CASE(false, true, 1) JSD_GEMM_CASE(true, false, 1) JSD_GEMM_CASE(true, true, 1)
   JSD_GEMM_CASE(false, false, 2) JSD_GEMM_CASE(false, true, 2) JSD_GEMM_CASE(true, false, 2) JSD_GEMM_CASE(true, true, 2)
 #undef JSD_GEMM_CASE
@@ -276,7 +292,7 @@ int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; 
 
 extern "C" {
 
-int jsd_abi_version(void) { return 6; }
+int jsd_abi_version(void) { return 7; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -415,13 +431,67 @@ extern "C" {
 
 size_t jsd_streamk_flag_bytes(void) { return streamk_flag_bytes(); }
 
+// split-K partial slices of an underfilled GRAD launch: (ksplit - 1) * rows * D floats with tiles * ksplit <= 74 CTA
+// pairs, i.e. at most 74 * 256 * 256 floats; two regions (dU and dV of one step may be live together)
+constexpr size_t kSplitRegionBytes = (size_t)80 * 256 * 256 * sizeof(float);
+
 size_t jsd_streamk_workspace_bytes(void) {
-  return streamk_flag_bytes() + (size_t)jsd::SK_MAX_CTAS * jsd::SK_SLOT_FLOATS * sizeof(float);
+  const size_t sk = (size_t)jsd::SK_MAX_CTAS * jsd::SK_SLOT_FLOATS * sizeof(float);
+  return streamk_flag_bytes() + (sk > 2 * kSplitRegionBytes ? sk : 2 * kSplitRegionBytes);
+}
+
+// Split-K plan of an underfilled GRAD launch whose consumer is the library's own Jacobian kernel: when the output
+// tiles fill at most half of the CTA pairs (dU of a 1024-row rank: 16 tiles for 74 pairs), every tile is computed
+// in `ksplit` K-slices by different workers; the slices land in `region` of the workspace and the Jacobian kernel
+// adds them in order (NormBwdJob::slot).  ksplit = 1: nothing to do.
+struct SplitPlan {
+  int ksplit = 1;
+  float* slice_base = nullptr;
+  long long slice_stride = 0;
+};
+
+static SplitPlan plan_split(int64_t rows, int64_t D, int64_t kdim, void* workspace, int region) {
+  SplitPlan sp;
+  static int enabled = -1;                                     // development knob: JSD_SPLITK=0 disables it
+  if (enabled < 0) {
+    const char* e = getenv("JSD_SPLITK");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || workspace == nullptr) return sp;
+  const int cg = pick_cta_group(rows);
+  const int workers = sm_count_cached() / cg;
+  const long long tiles = ((rows + jsd::BLOCK_M * cg - 1) / (jsd::BLOCK_M * cg)) * ((D + jsd::BLOCK_N - 1) / jsd::BLOCK_N);
+  const long long nk = (kdim + jsd::BLOCK_K * jsd::k_atoms(jsd::MODE_GRAD) - 1) / (jsd::BLOCK_K * jsd::k_atoms(jsd::MODE_GRAD));
+  if (tiles <= 0 || tiles * 2 > workers) return sp;
+  long long kmax = workers / tiles;
+  if (kmax > 8) kmax = 8;                                      // NormBwdJob sums at most 8 slices
+  if (kmax > nk / 2) kmax = nk / 2;                            // at least two k-chunks per slice
+  // Cost model (measured on B200): a k-chunk of a 256 x 256 pair tile takes ~0.7 us, so s slices save
+  // (1 - 1/s) nk 0.7 us of serial MMA time; every extra slice is rows x D fp32 written by the GEMM and read back by
+  // the Jacobian kernel (~3 TB/s effective).  B = 1024, D = 1024 single GPU: splitting loses (measured 61 -> 68 us
+  // per step); dU of a 1024-row rank against 8192 text rows: 53 -> 30 us.
+  long long ks = 1;
+  double best = 2.0;                                           // demand at least 2 us of gain
+  for (long long c = 2; c <= kmax; ++c) {
+    const double gain = (1.0 - 1.0 / (double)c) * (double)nk * 0.7 -
+                        (double)(c - 1) * (double)rows * (double)D * 8.0 / 3.0e6;
+    if (gain > best) {
+      best = gain;
+      ks = c;
+    }
+  }
+  if (ks < 2) return sp;
+  if ((size_t)(ks - 1) * rows * D * sizeof(float) > kSplitRegionBytes) return sp;
+  sp.ksplit = (int)ks;
+  sp.slice_base = reinterpret_cast<float*>(static_cast<char*>(workspace) + streamk_flag_bytes() + region * kSplitRegionBytes);
+  sp.slice_stride = rows * D;
+  return sp;
 }
 
 static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* X, int64_t M, int64_t N, int64_t D,
                             const float* t_dev, const float* gamma_dev, void* sk_workspace, float* out,
-                            jsd_stream_t stream, const jsd_peer_ctx* peer = nullptr) {
+                            jsd_stream_t stream, const jsd_peer_ctx* peer = nullptr, int sk_policy = SK_RAGGED,
+                            const SplitPlan* split = nullptr) {
   JSD_REQUIRE(Gmat && X && t_dev && (out || peer), "jsd_dense_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_bwd: M=%lld N=%lld D=%lld out of range",
               (long long)M, (long long)N, (long long)D);
@@ -446,6 +516,13 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
   p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;
   p.out = out;
   p.ldo = D;
+  p.ksplit = 1;
+  if (split != nullptr && split->ksplit > 1) {
+    p.ksplit = split->ksplit;
+    p.slice_base = split->slice_base;
+    p.slice_stride = split->slice_stride;
+    sk_workspace = nullptr;                                    // split-K and stream-K are exclusive
+  }
   if (peer != nullptr) {
     // the partial over ALL text rows stays in this rank's (peer-mapped) buffer; the owner of each row block
     // reads it from there once this launch has published its flag
@@ -457,7 +534,7 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
     p.peer_ticket = mine + JSD_PEER_TICKET_DV;
   }
   return launch_gemm_any<jsd::MODE_GRAD>(dv, true, pick_cta_group(rows), tmA, tmB, p, sk_workspace,
-                                          (cudaStream_t)stream);
+                                          (cudaStream_t)stream, sk_policy);
 }
 
 int jsd_dense_bwd_du(const void* Gmat, int64_t ldg, const void* V, int64_t M, int64_t N, int64_t D,
@@ -472,10 +549,23 @@ int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, int64_t M, in
   return dense_bwd_common(true, Gmat, ldg, U, M, N, D, t_dev, gamma_dev, sk_workspace, dVacc, stream);
 }
 
+static int normalize_bwd_impl(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm,
+                              const float* acc, const SplitPlan* split, const void* partner, int64_t partner_offset,
+                              const float* gdiag, const float* t_dev, const float* gamma_dev, int64_t M_rows, void* dX,
+                              float* rowdot, void* workspace, float* dt_out, jsd_stream_t stream);
+
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
                       const float* gamma_dev, int64_t M_rows, void* dX, float* rowdot, void* workspace, float* dt_out,
                       jsd_stream_t stream) {
+  return normalize_bwd_impl(X, dtype, rows, D, inv_norm, acc, nullptr, partner, partner_offset, gdiag, t_dev, gamma_dev,
+                            M_rows, dX, rowdot, workspace, dt_out, stream);
+}
+
+static int normalize_bwd_impl(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm,
+                              const float* acc, const SplitPlan* split, const void* partner, int64_t partner_offset,
+                              const float* gdiag, const float* t_dev, const float* gamma_dev, int64_t M_rows, void* dX,
+                              float* rowdot, void* workspace, float* dt_out, jsd_stream_t stream) {
   JSD_REQUIRE(X && inv_norm && acc && partner && t_dev && dX, "jsd_normalize_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(rows) && fits_int(D) && M_rows > 0, "jsd_normalize_bwd: bad shape");
   JSD_REQUIRE(dt_out == nullptr || (rowdot && workspace), "jsd_normalize_bwd: dt_out needs rowdot and the workspace");
@@ -489,6 +579,11 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
   job.rowdot = rowdot;
   job.ticket = dt_out ? dt_ticket(workspace) : nullptr;
   job.dt_out = dt_out;
+  if (split != nullptr && split->ksplit > 1) {          // the accumulator is the sum of the split-K slices, in order
+    job.acc_slots = split->ksplit;
+    job.slot[0] = acc;
+    for (int q = 1; q < split->ksplit; ++q) job.slot[q] = split->slice_base + (size_t)(q - 1) * split->slice_stride;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_rows = (float)(1.0 / (double)M_rows);
   JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 1, rows, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
@@ -504,27 +599,34 @@ int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_
 int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U, const void* V,
                        const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg, const float* gdiag,
                        const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v, float* rowdot,
-                       void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
+                       void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
   JSD_REQUIRE(F && G && U && V && inv_f && inv_g && gdiag && dF && dG, "jsd_dense_backward: null pointer argument");
   JSD_REQUIRE(dt_out && acc_u && acc_v && rowdot && workspace, "jsd_dense_backward: null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = jsd_dense_bwd_du(Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
+  const SplitPlan su = plan_split(B, D, B, sk_workspace, 0), sv = plan_split(B, D, B, sk_workspace, 1);
+  if (int rc = dense_bwd_common(false, Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0, &su))
+    return rc;
   SideStream* side = side_stream();
-  if (side != nullptr) {
+  if (side != nullptr || su.ksplit > 1 || sv.ksplit > 1) {
     // image-side Jacobian (+ gamma * dL/dt) on the helper stream, next to the dV contraction.  The contraction
     // is enqueued FIRST so that its persistent CTAs take the SMs and the Jacobian's blocks fill in as they retire.
-    JSD_CUDA_OK(cudaEventRecord(side->fork, st));
-    if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
-    JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    if (int rc = jsd_normalize_bwd(F, dtype, B, D, inv_f, acc_u, V, 0, gdiag, t_dev, gamma_dev, B, dF, rowdot,
-                                   workspace, dt_out, side->stream))
+    cudaStream_t js = side ? side->stream : st;
+    if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
+    if (int rc = dense_bwd_common(true, Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream, nullptr, 0, &sv))
       return rc;
-    JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
-    JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
-    return jsd_normalize_bwd(G, dtype, B, D, inv_g, acc_v, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, nullptr,
-                             nullptr, stream);
+    if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if (int rc = normalize_bwd_impl(F, dtype, B, D, inv_f, acc_u, &su, V, 0, gdiag, t_dev, gamma_dev, B, dF, rowdot,
+                                    workspace, dt_out, js))
+      return rc;
+    if (side) {
+      JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
+      JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+    }
+    return normalize_bwd_impl(G, dtype, B, D, inv_g, acc_v, &sv, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, nullptr,
+                              nullptr, stream);
   }
-  if (int rc = jsd_dense_bwd_dv(Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream)) return rc;
+  if (int rc = dense_bwd_common(true, Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream, nullptr, 0, &sv))
+    return rc;
   // both Jacobians (image side = job 0, text side = job 1) and gamma * dL/dt = sum_i <u_i, dU_i> in one launch
   jsd::NormBwdJob job{};
   job.X[0] = F;
@@ -547,11 +649,15 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
 int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                                   const void* V_all, const float* inv_f, const void* Gmat, int64_t ldg,
                                   const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                                  float* rowdot, void* workspace, void* dF, float* dt_out, jsd_stream_t stream) {
+                                  float* rowdot, void* workspace, void* sk_workspace, void* dF, float* dt_out,
+                                  jsd_stream_t stream) {
   JSD_REQUIRE(acc_u && rowdot && dt_out && workspace, "jsd_dense_backward_image_side: null pointer argument");
-  if (int rc = jsd_dense_bwd_du(Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
-  return jsd_normalize_bwd(F, dtype, M, D, inv_f, acc_u, V_all, row_offset, gdiag, t_dev, gamma_dev, M, dF, rowdot,
-                           workspace, dt_out, stream);
+  const SplitPlan su = plan_split(M, D, N, sk_workspace, 0);
+  if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0,
+                                &su))
+    return rc;
+  return normalize_bwd_impl(F, dtype, M, D, inv_f, acc_u, &su, V_all, row_offset, gdiag, t_dev, gamma_dev, M, dF,
+                            rowdot, workspace, dt_out, stream);
 }
 
 /* ------------------------------------------------------------------ peer-memory exchange */
@@ -657,10 +763,11 @@ int jsd_peer_dense_fwd(const void* U, const jsd_peer_ctx* ctx, int parity, const
 }
 
 int jsd_peer_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
-                          const float* gamma_dev, jsd_stream_t stream) {
+                          const float* gamma_dev, void* sk_workspace, jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_bwd_dv")) return rc;
+  (void)sk_workspace;                // the partial is read by the peers as one buffer: whole tiles only
   return dense_bwd_common(true, Gmat, ldg, U, ctx->rows, ctx->rows * ctx->world, ctx->dim, t_dev, gamma_dev, nullptr,
-                          nullptr, stream, ctx);
+                          nullptr, stream, ctx, 0);
 }
 
 int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g, const void* U,
@@ -690,20 +797,24 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
 int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
                             const void* U, const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg,
                             const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                            float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
+                            float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out,
+                            jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_backward")) return rc;
   JSD_REQUIRE(parity == 0 || parity == 1, "jsd_peer_dense_backward: parity must be 0 or 1");
   const void* V_all = ctx->v_all[parity][ctx->rank];
   const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim, off = ctx->rows * ctx->rank;
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = jsd_dense_bwd_du(Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream)) return rc;
+  const SplitPlan su = plan_split(M, D, N, sk_workspace, 0);
+  if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0,
+                                &su))
+    return rc;
   SideStream* side = side_stream();
   cudaStream_t js = side ? side->stream : st;       // image-side Jacobian next to the dV contraction (enqueued first)
   if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
-  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, stream)) return rc;
+  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, sk_workspace, stream)) return rc;
   if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  if (int rc = jsd_normalize_bwd(F, dtype, M, D, inv_f, acc_u, V_all, off, gdiag, t_dev, gamma_dev, M, dF, rowdot,
-                                 workspace, dt_out, js))
+  if (int rc = normalize_bwd_impl(F, dtype, M, D, inv_f, acc_u, &su, V_all, off, gdiag, t_dev, gamma_dev, M, dF,
+                                  rowdot, workspace, dt_out, js))
     return rc;
   if (side) {
     JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));

@@ -107,6 +107,12 @@ struct GemmParams {
   int stream_k;
   int* sk_flags;
   float* sk_slots;
+  // split-K (GRAD, whole tiles): each output tile is computed `ksplit` times over consecutive K ranges by
+  // different workers; slice 0 goes to `out`, slice s > 0 to slice_base + (s - 1) * slice_stride (same pitch).
+  // The consumer (the Jacobian kernel) adds the slices in order: deterministic, no atomics, no hand-off flags.
+  int ksplit;
+  float* slice_base;
+  long long slice_stride;
   // SCORE (retrieval / zero-shot scoring, S = A B^T never stored).  Pass 0 extracts the target scores, pass 1
   // counts the entries that beat them -- the same tiles, the same accumulation order, so a target never beats
   // itself and no tie margin is needed.
@@ -192,14 +198,15 @@ __device__ __forceinline__ float dec_ordered(unsigned e) {
 //      fraction of a tile, a tile split between groups is finished by the group holding its head;
 //   2. the remaining m-blocks are whole tiles, one wave after the other.
 struct SegmentIter {
-  int num_k, num_tiles, stride, tile;   // round-robin whole tiles
+  int num_k, num_tiles, stride, tile;   // round-robin whole tiles (x ksplit K-slices)
+  int ksplit, slice;                    // split-K: slices per tile, slice of the segment last returned
   int n_blocks, n_blk;                  // stream-K: column blocks per m-block, this worker's column block
   int groups, group, sk_mb, dp_i, dp_waves;
   long long u, u_end;                   // stream-K: unit range of this worker's group in the sk_mb space
   bool stream_k;
-  __device__ SegmentIter(bool sk, int worker, int n_workers, int tiles, int nk, int nb)
-      : num_k(nk), num_tiles(tiles), stride(n_workers), tile(worker), n_blocks(nb), n_blk(0), groups(1), group(0),
-        sk_mb(0), dp_i(0), dp_waves(0), u(0), u_end(0), stream_k(sk) {
+  __device__ SegmentIter(bool sk, int worker, int n_workers, int tiles, int nk, int nb, int ks = 1)
+      : num_k(nk), num_tiles(tiles), stride(n_workers), tile(worker), ksplit(ks < 1 ? 1 : ks), slice(0), n_blocks(nb),
+        n_blk(0), groups(1), group(0), sk_mb(0), dp_i(0), dp_waves(0), u(0), u_end(0), stream_k(sk) {
     if (sk) {
       groups = n_workers / nb;
       group = worker / nb;
@@ -237,10 +244,11 @@ struct SegmentIter {
       }
       return false;
     }
-    if (tile >= num_tiles) return false;
-    t = tile;
-    k0 = 0;
-    k1 = num_k;
+    if (tile >= num_tiles * ksplit) return false;
+    t = tile / ksplit;                    // neighbouring workers share an output tile, each takes one K range
+    slice = tile - t * ksplit;
+    k0 = (int)((long long)slice * num_k / ksplit);
+    k1 = (int)((long long)(slice + 1) * num_k / ksplit);
     tile += stride;
     return true;
   }
@@ -338,7 +346,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         wait_flags_sys(p.wait_flags, p.wait_count, *p.wait_counter);
         fence_proxy_async_all();
       }
-      SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
+      SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
         int m_blk, n_blk;
@@ -380,7 +388,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
+      SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -447,7 +455,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks);
+    SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
     int tile, k0, k1;
     while (it.next(tile, k0, k1)) {
       int m_blk, n_blk;
@@ -660,7 +668,8 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (row_ok) {
-            float* dst = p.out + (long long)grow * p.ldo + col0;
+            float* obase = it.slice == 0 ? p.out : p.slice_base + (long long)(it.slice - 1) * p.slice_stride;
+            float* dst = obase + (long long)grow * p.ldo + col0;
             if (col0 + CW <= p.N) {
 #pragma unroll
               for (int k4 = 0; k4 < CW / 4; ++k4) {

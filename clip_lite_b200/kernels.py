@@ -106,32 +106,34 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
 
 
 # ------------------------------------------------------------------ dense mode
+# Scratch buffers of the dense path, one of each per DEVICE, allocated zeroed on first use and kept: the kernels
+# leave their flag / ticket words zero after every launch.  They are deliberately not per stream -- a CUDA-graph
+# capture must not allocate (and memset) 33 MB inside the graph, it re-uses the buffers of the eager warm-up --
+# so at most one dense step may be in flight per device at a time (steps on one stream, or graph replays, are).
 _SK_WORKSPACES = {}
-
-
-def streamk_workspace(device) -> torch.Tensor:
-    """Per (device, stream) scratch of the backward GEMMs (stream-K partial tiles + flags).
-    Allocated zeroed once; the kernels leave the flag area zero after every launch."""
-    key = (str(device), _stream())
-    ws = _SK_WORKSPACES.get(key)
-    if ws is None:
-        ws = torch.zeros(_lib.load().jsd_streamk_workspace_bytes(), dtype=torch.uint8, device=device)
-        _SK_WORKSPACES[key] = ws
-    return ws
-
-
 _FWD_WORKSPACES = {}
 
 
-def dense_workspace(device) -> torch.Tensor:
-    """Per (device, stream) scratch of the forward kernel: a finalisation ticket (must be zero between
-    launches; the kernel re-zeroes it) followed by the per-warp loss partials.  Allocated zeroed once."""
-    key = (str(device), _stream())
-    ws = _FWD_WORKSPACES.get(key)
+def _device_workspace(cache: dict, nbytes: int, device) -> torch.Tensor:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ws = cache.get(key)
     if ws is None:
-        ws = torch.zeros(_lib.load().jsd_dense_workspace_bytes(), dtype=torch.uint8, device=device)
-        _FWD_WORKSPACES[key] = ws
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("run one eager step of the dense path before capturing it into a CUDA graph "
+                               "(its scratch buffers are allocated on first use)")
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        cache[key] = ws
     return ws
+
+
+def streamk_workspace(device) -> torch.Tensor:
+    """Scratch of the backward contractions (stream-K partial tiles + hand-off flags, 33 MB)."""
+    return _device_workspace(_SK_WORKSPACES, _lib.load().jsd_streamk_workspace_bytes(), device)
+
+
+def dense_workspace(device) -> torch.Tensor:
+    """Scratch of the forward / Jacobian kernels: "last block" tickets followed by the per-warp loss partials."""
+    return _device_workspace(_FWD_WORKSPACES, _lib.load().jsd_dense_workspace_bytes(), device)
 
 
 def normalize_cast(x: torch.Tensor):
@@ -210,7 +212,8 @@ def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: tor
         _lib.call("jsd_dense_backward", f.data_ptr(), g.data_ptr(), _code(f), b, d, u.data_ptr(), v.data_ptr(),
                   inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
                   tt.data_ptr(), gg.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(), small.data_ptr(),
-                  ws.data_ptr(), df.data_ptr(), dg.data_ptr(), small[b:].data_ptr(), _stream())
+                  ws.data_ptr(), streamk_workspace(dev).data_ptr(), df.data_ptr(), dg.data_ptr(),
+                  small[b:].data_ptr(), _stream())
     return df, dg, small[b]
 
 
@@ -298,7 +301,8 @@ def dense_backward_image_side(f, v_all, inv_f, gmat, gdiag, t, gamma, row_offset
         ws = dense_workspace(dev)
         _lib.call("jsd_dense_backward_image_side", f.data_ptr(), _code(f), m, n, d, row_offset, v_all.data_ptr(),
                   inv_f.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(), tt.data_ptr(), gg.data_ptr(),
-                  acc.data_ptr(), small.data_ptr(), ws.data_ptr(), df.data_ptr(), small[m:].data_ptr(), _stream())
+                  acc.data_ptr(), small.data_ptr(), ws.data_ptr(), streamk_workspace(dev).data_ptr(), df.data_ptr(),
+                  small[m:].data_ptr(), _stream())
     return df, small[m]
 
 

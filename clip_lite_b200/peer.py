@@ -130,7 +130,7 @@ class PeerExchange:
     def dense_bwd_dv(self, gmat: torch.Tensor, u: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor):
         tt, gg = K._scalar(t, "temperature"), K._scalar(gamma, "gamma")
         _lib.call("jsd_peer_dense_bwd_dv", gmat.data_ptr(), gmat.shape[1], u.data_ptr(), self._ctx_ptr,
-                  tt.data_ptr(), gg.data_ptr(), K._stream())
+                  tt.data_ptr(), gg.data_ptr(), K.streamk_workspace(gmat.device).data_ptr(), K._stream())
 
     def dense_backward(self, f, g, t, gamma, parity: int, u, inv_f, inv_g, gmat, gdiag):
         """Whole backward of a step in one library call.  Returns (dF, dG, dt)."""
@@ -142,8 +142,9 @@ class PeerExchange:
         ws = K.dense_workspace(f.device)
         _lib.call("jsd_peer_dense_backward", f.data_ptr(), g.data_ptr(), K._code(f), self._ctx_ptr, parity,
                   u.data_ptr(), inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
-                  tt.data_ptr(), gg.data_ptr(), acc.data_ptr(), small.data_ptr(), ws.data_ptr(), df.data_ptr(),
-                  dg.data_ptr(), small[m:].data_ptr(), K._stream())
+                  tt.data_ptr(), gg.data_ptr(), acc.data_ptr(), small.data_ptr(), ws.data_ptr(),
+                  K.streamk_workspace(f.device).data_ptr(), df.data_ptr(), dg.data_ptr(), small[m:].data_ptr(),
+                  K._stream())
         return df, dg, small[m]
 
     def normalize_bwd_text(self, g: torch.Tensor, inv_g, u, gdiag, t, gamma) -> torch.Tensor:

@@ -89,7 +89,11 @@ int jsd_dense_fwd(const void* U_bf16, const void* V_bf16, int64_t M, int64_t N, 
                   const float* t_dev, void* Gmat_bf16, int64_t ldg, float* gdiag, void* workspace, float* out4,
                   float* loss_out, jsd_stream_t stream);
 
-/* Workspace of the backward contractions (stream-K partial tiles + hand-off flags).  The first
+/* Stream-K: the backward contractions can cut tiles along the contraction so that every CTA pair has work.
+ * Passing `sk_workspace` (NULL = never) allows it; the single-call backward entry points below use it only when the
+ * tiles fill at most half of the GPU (e.g. dU of a 1024-row rank: 16 tiles for 74 CTA pairs, 4.5x faster split),
+ * jsd_dense_bwd_du/dv and jsd_gemm_bf16 additionally to balance a ragged last wave.
+ * Workspace of the backward contractions (stream-K partial tiles + hand-off flags).  The first
  * jsd_streamk_flag_bytes() bytes must be ZERO when the buffer is first used; every launch leaves
  * them zero again.  One buffer per concurrently used stream. */
 size_t jsd_streamk_workspace_bytes(void);
@@ -133,7 +137,8 @@ int jsd_dense_forward(const void* F, const void* G, int dtype, int64_t B, int64_
 int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U_bf16,
                        const void* V_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16, int64_t ldg,
                        const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u, float* acc_v,
-                       float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
+                       float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out,
+                       jsd_stream_t stream);
 
 /* Row-slab (multi-GPU) convenience calls: one FFI crossing each.
  *   jsd_normalize_cast_pair       = jsd_normalize_cast of F and of G in one launch
@@ -144,7 +149,8 @@ int jsd_normalize_cast_pair(const void* F, const void* G, int dtype, int64_t row
 int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                                   const void* V_all_bf16, const float* inv_f, const void* Gmat_bf16, int64_t ldg,
                                   const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                                  float* rowdot, void* workspace, void* dF, float* dt_out, jsd_stream_t stream);
+                                  float* rowdot, void* workspace, void* sk_workspace, void* dF, float* dt_out,
+                                  jsd_stream_t stream);
 
 /* ------------------------------------------------------------------ peer-memory exchange (multi-GPU dense path)
  * One process per GPU; the two exchange steps of the sharded path (all-gather of the text rows, sum of
@@ -195,7 +201,7 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
 int jsd_peer_dense_fwd(const void* U_bf16, const jsd_peer_ctx* ctx, int parity, const float* t_dev, void* Gmat_bf16,
                        int64_t ldg, float* gdiag, void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
 int jsd_peer_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, const jsd_peer_ctx* ctx,
-                          const float* t_dev, const float* gamma_dev, jsd_stream_t stream);
+                          const float* t_dev, const float* gamma_dev, void* sk_workspace, jsd_stream_t stream);
 int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g,
                                 const void* U_bf16, const float* gdiag, const float* t_dev, const float* gamma_dev,
                                 void* dG, jsd_stream_t stream);
@@ -206,7 +212,8 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
 int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
                             const void* U_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16,
                             int64_t ldg, const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                            float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
+                            float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out,
+                            jsd_stream_t stream);
 
 /* ------------------------------------------------------------------ retrieval / zero-shot scoring
  * replaces: retrieval.py:143 (`sims_matrix = image_embeds @ text_embeds.t()`, copied to the host) + the NumPy

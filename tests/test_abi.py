@@ -41,7 +41,7 @@ def test_python_binding_covers_every_declared_symbol():
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.jsd_abi_version() == 6
+    assert lib.jsd_abi_version() == 7
     assert lib.jsd_last_error() is not None
     # argument validation happens before any CUDA call: a null pointer is refused with a message
     rc = lib.jsd_dense_fwd(None, None, 8, 8, 8, 0, None, None, 0, None, None, None, None, None)

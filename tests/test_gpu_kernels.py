@@ -275,7 +275,12 @@ def test_fused_forward_backward_calls_equal_the_staged_calls(K, dtype):
     dfb, dtb = K.normalize_bwd(f, inv_f, du, v, 0, gdiag, t, gamma, b, want_dt=True)
     dgb = K.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, b)
     assert torch.equal(out4, out4b) and torch.equal(loss, lossb)
-    assert torch.equal(df, dfb) and torch.equal(dg, dgb) and torch.equal(dt, dtb)
+    # at this size the fused backward splits the contraction of its underfilled GEMM launches over idle CTA pairs
+    # (split-K, slices added in a fixed order): same arithmetic, different fp32 summation order than the staged calls
+    tol = 1e-5 if dtype == torch.float32 else 8e-3        # 16-bit outputs: the last fp32 bits can flip one rounding
+    assert relerr(df, dfb) < tol and relerr(dg, dgb) < tol and relerr(dt, dtb) < 1e-5
+    df2, dg2, dt2 = K.dense_backward(f, g, t, gamma, saved)
+    assert torch.equal(df, df2) and torch.equal(dg, dg2) and torch.equal(dt, dt2)      # and it is deterministic
     _, _, rdt = orc.jsd_dense_grads(f.double(), g.double(), T0, gamma=0.7)
     assert relerr(dt, rdt) < GRAD_RTOL
 
@@ -294,4 +299,6 @@ def test_slab_convenience_calls_equal_the_staged_calls(K):
     df, dt = K.dense_backward_image_side(fl, v_all, inv_f, gmat, gdiag, t, gamma, off)
     du = K.dense_bwd_du(gmat, v_all, t, gamma)
     dfb, dtb = K.normalize_bwd(fl, inv_f, du, v_all, off, gdiag, t, gamma, m, want_dt=True)
-    assert torch.equal(df, dfb) and torch.equal(dt, dtb)
+    assert relerr(df, dfb) < 1e-5 and relerr(dt, dtb) < 1e-5      # split-K in the fused call: other summation order
+    df2, dt2 = K.dense_backward_image_side(fl, v_all, inv_f, gmat, gdiag, t, gamma, off)
+    assert torch.equal(df, df2) and torch.equal(dt, dt2)

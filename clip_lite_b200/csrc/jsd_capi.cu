@@ -804,23 +804,28 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
   const void* V_all = ctx->v_all[parity][ctx->rank];
   const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim, off = ctx->rows * ctx->rank;
   cudaStream_t st = (cudaStream_t)stream;
+  // 1. the text-side partial first: its "complete" flag reaches the peers as early as possible
+  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, sk_workspace, stream)) return rc;
+  SideStream* side = side_stream();
+  if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
+  // 2. the image-side contraction (split-K when a rank's rows underfill the GPU) ...
   const SplitPlan su = plan_split(M, D, N, sk_workspace, 0);
   if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0,
                                 &su))
     return rc;
-  SideStream* side = side_stream();
-  cudaStream_t js = side ? side->stream : st;       // image-side Jacobian next to the dV contraction (enqueued first)
-  if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
-  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, sk_workspace, stream)) return rc;
+  // 3. ... and NEXT TO it, on the helper stream, the text-side Jacobian: it waits for the peers' flags and pulls
+  //    their partials over NVLink (link-bound, needs few SMs: it runs on the CTA pairs the contraction leaves idle
+  //    and spreads out once that retires).  Enqueued after the contraction so that the latter gets its SMs first.
+  cudaStream_t ts = side ? side->stream : st;
   if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  if (int rc = jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, dG, ts)) return rc;
+  if (side) JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
+  // 4. image-side Jacobian (+ gamma * dL_r/dt) behind the contraction
   if (int rc = normalize_bwd_impl(F, dtype, M, D, inv_f, acc_u, &su, V_all, off, gdiag, t_dev, gamma_dev, M, dF,
-                                  rowdot, workspace, dt_out, js))
+                                  rowdot, workspace, dt_out, stream))
     return rc;
-  if (side) {
-    JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
-    JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
-  }
-  return jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, dG, stream);
+  if (side) JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+  return 0;
 }
 
 /* ------------------------------------------------------------------ retrieval / zero-shot scoring */

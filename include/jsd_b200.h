@@ -206,9 +206,11 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
                                 const void* U_bf16, const float* gdiag, const float* t_dev, const float* gamma_dev,
                                 void* dG, jsd_stream_t stream);
 
-/* Whole backward of a peer-exchange step in one call: dU contraction, then the image-side Jacobian (+ dt_out =
- * gamma * dL_r/dt) on a helper stream NEXT TO the dV contraction (whose ragged last wave leaves SMs idle), then the
- * text-side Jacobian (pull).  acc_u fp32 [rows, D] and rowdot fp32 [rows] are scratch; workspace = the forward's. */
+/* Whole backward of a peer-exchange step in one call: the dV partial first (its flag goes out early), then the dU
+ * contraction (split-K when the rank's rows underfill the GPU) with -- on a library-owned helper stream NEXT TO
+ * it -- the text-side Jacobian that waits for the peers and pulls their partials over NVLink, then the image-side
+ * Jacobian (+ dt_out = gamma * dL_r/dt).  acc_u fp32 [rows, D] and rowdot fp32 [rows] are scratch; workspace =
+ * the forward's; sk_workspace = jsd_streamk_workspace_bytes() bytes (split-K slices). */
 int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
                             const void* U_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16,
                             int64_t ldg, const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,

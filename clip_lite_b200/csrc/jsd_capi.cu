@@ -552,7 +552,8 @@ int jsd_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, int64_t M, in
 static int normalize_bwd_impl(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm,
                               const float* acc, const SplitPlan* split, const void* partner, int64_t partner_offset,
                               const float* gdiag, const float* t_dev, const float* gamma_dev, int64_t M_rows, void* dX,
-                              float* rowdot, void* workspace, float* dt_out, jsd_stream_t stream);
+                              float* rowdot, void* workspace, float* dt_out, jsd_stream_t stream,
+                              const float* reduce_src = nullptr, int64_t reduce_n = 0, float* reduce_out = nullptr);
 
 int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm, const float* acc,
                       const void* partner, int64_t partner_offset, const float* gdiag, const float* t_dev,
@@ -565,7 +566,8 @@ int jsd_normalize_bwd(const void* X, int dtype, int64_t rows, int64_t D, const f
 static int normalize_bwd_impl(const void* X, int dtype, int64_t rows, int64_t D, const float* inv_norm,
                               const float* acc, const SplitPlan* split, const void* partner, int64_t partner_offset,
                               const float* gdiag, const float* t_dev, const float* gamma_dev, int64_t M_rows, void* dX,
-                              float* rowdot, void* workspace, float* dt_out, jsd_stream_t stream) {
+                              float* rowdot, void* workspace, float* dt_out, jsd_stream_t stream,
+                              const float* reduce_src, int64_t reduce_n, float* reduce_out) {
   JSD_REQUIRE(X && inv_norm && acc && partner && t_dev && dX, "jsd_normalize_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(rows) && fits_int(D) && M_rows > 0, "jsd_normalize_bwd: bad shape");
   JSD_REQUIRE(dt_out == nullptr || (rowdot && workspace), "jsd_normalize_bwd: dt_out needs rowdot and the workspace");
@@ -579,6 +581,9 @@ static int normalize_bwd_impl(const void* X, int dtype, int64_t rows, int64_t D,
   job.rowdot = rowdot;
   job.ticket = dt_out ? dt_ticket(workspace) : nullptr;
   job.dt_out = dt_out;
+  job.reduce_src = reduce_src;
+  job.reduce_n = (int)reduce_n;
+  job.reduce_out = reduce_src ? reduce_out : nullptr;
   if (split != nullptr && split->ksplit > 1) {          // the accumulator is the sum of the split-K slices, in order
     job.acc_slots = split->ksplit;
     job.slot[0] = acc;
@@ -615,15 +620,17 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
     if (int rc = dense_bwd_common(true, Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream, nullptr, 0, &sv))
       return rc;
     if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    // the image side only stores its row dots; gamma * dL/dt = their sum is formed by block 0 of the text-side
+    // launch, which is stream-ordered behind it: no ticket, no device-wide fence in either kernel
     if (int rc = normalize_bwd_impl(F, dtype, B, D, inv_f, acc_u, &su, V, 0, gdiag, t_dev, gamma_dev, B, dF, rowdot,
-                                    workspace, dt_out, js))
+                                    nullptr, nullptr, js))
       return rc;
     if (side) {
       JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
       JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
     }
     return normalize_bwd_impl(G, dtype, B, D, inv_g, acc_v, &sv, U, 0, gdiag, t_dev, gamma_dev, B, dG, nullptr, nullptr,
-                              nullptr, stream);
+                              nullptr, stream, rowdot, B, dt_out);
   }
   if (int rc = dense_bwd_common(true, Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v, stream, nullptr, 0, &sv))
     return rc;

@@ -414,6 +414,20 @@ normalize_push_kernel(const PeerPushJob job, int rows, int D) {
   }
 }
 
+// Fixed-order fp64 sum of n floats by one block (deterministic); every thread of the block must call it.
+__device__ __forceinline__ void block_reduce_to(const float* src, int n, float* out) {
+  __shared__ double s_red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)__ldcg(src + i);
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)s_red[0];
+}
+
 // Last-block reduction of the row dots: dt_out = sum_i rowdot[i] (fp64, fixed order => deterministic).
 // Called by every thread of every block at the end of a normalise-backward kernel when dt_out != nullptr.
 __device__ __forceinline__ void reduce_rowdot_last_block(const float* rowdot, int rows, int* ticket, float* dt_out) {
@@ -459,6 +473,11 @@ struct NormBwdJob {
   // each rank's memory (slot[q], read over NVLink, already offset to this rank's rows), added here in rank order
   // (deterministic) -- the reduce-scatter is fused into its consumer.  Every block first waits until each rank's
   // flag has reached *wait_counter ("my partial is complete").
+  // deferred dL/dt: block (0, 0) of THIS launch sums reduce_src[0 .. reduce_n) -- row dots written by an EARLIER
+  // launch (stream order makes them visible) -- into *reduce_out: no ticket, no fence in either kernel
+  const float* reduce_src;
+  int reduce_n;
+  float* reduce_out;
   int acc_slots;               // 0: a single local accumulator (acc[])
   const float* slot[8];
   const int* wait_flags;       // null: no wait
@@ -528,7 +547,7 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   dot = warp_sum(dot) * inv;   // <u, dU>
   if (rowdot != nullptr && lane == 0) {   // sum over rows = gamma * dL/dt
     rowdot[row] = dot;
-    __threadfence();                      // published now: the fence must not wait for the row's big stores below
+    if (job.dt_out != nullptr) __threadfence();   // ticketed reduction in this launch: publish now, not after the row's big stores
   }
   T* o = dX + (size_t)row * D;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
@@ -546,6 +565,7 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   });
   }  // row < rows
   if (job.dt_out != nullptr) reduce_rowdot_last_block(job.rowdot, rows, job.ticket, job.dt_out);
+  if (job.reduce_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0) block_reduce_to(job.reduce_src, job.reduce_n, job.reduce_out);
 }
 
 // ------------------------------------------------------------------ register-resident variants (D = nch * 128 <= 1024)
@@ -646,7 +666,7 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
   dot = warp_sum(dot) * inv;   // <u, dU>
   if (rowdot != nullptr && lane == 0) {
     rowdot[row] = dot;
-    __threadfence();                      // published now: the fence must not wait for the row's big stores below
+    if (job.dt_out != nullptr) __threadfence();   // ticketed reduction in this launch: publish now, not after the row's big stores
   }
   T* o = dX + (size_t)row * D + lane * 4;
   const float k = inv * dot;
@@ -662,6 +682,7 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
     }
   }  // row < rows
   if (job.dt_out != nullptr) reduce_rowdot_last_block(job.rowdot, rows, job.ticket, job.dt_out);
+  if (job.reduce_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0) block_reduce_to(job.reduce_src, job.reduce_n, job.reduce_out);
 }
 
 }  // namespace jsd

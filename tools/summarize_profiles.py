@@ -42,13 +42,14 @@ def launches():
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     seq = [(short(r[ki]), float(r[vi].replace(",", "")) / 1000.0) for r in data if len(r) > vi]
-    # one steady-state step = the launches between two consecutive forward GEMMs (mode 0)
-    fwd = [i for i, (n, _) in enumerate(seq) if n.startswith("jsd_gemm_kernel<0")]
+    # one steady-state step = the launches from one normalise pre-pass to the next
+    starts = [i for i, (n, _) in enumerate(seq) if n.startswith("normalize_cast")]
     lines = ["# ncu --metrics gpu__time_duration.sum --clock-control none (python bench.py --steps 3 --warmup 3)",
              "# per-launch device time, serialised and cold-cache: compare SHARES, not absolutes", ""]
-    if len(fwd) >= 3:
-        a, b = fwd[1], fwd[2]
-        step = seq[a - 2:b - 2]           # the two normalize_cast launches precede the forward GEMM
+    steps = [(a, b) for a, b in zip(starts, starts[1:]) if any(n.startswith("jsd_gemm_kernel<0") for n, _ in seq[a:b])]
+    if len(steps) >= 3:
+        a, b = steps[len(steps) // 2]
+        step = [(n, t) for n, t in seq[a:b] if "FillFunctor<unsigned char>" not in n]   # drop bench.py's L2 flush
         total = sum(t for _, t in step)
         lines.append(f"## one step ({len(step)} launches, {total:.1f} us of kernel time)")
         for n, t in step:

@@ -422,9 +422,9 @@ def run_b200(args, wl):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = time_cpu(batch, dim, budget_s=20.0)
-        # library launches per step -- 1 GPU: normalise pair, fwd (+ loss), dU, dV, both Jacobians (+ dL/dt);
-        # N GPUs: normalise(+push), fwd, dU, image Jacobian, dV(+push), text Jacobian
-        launches_per_step = 5 if world == 1 else 6
+        # library launches per step: normalise pair (+push), forward (+ loss), dU, dV, image Jacobian (helper
+        # stream), text Jacobian (+ dL/dt); with JSD_OVERLAP=0 one GPU runs both Jacobians in one launch
+        launches_per_step = 5 if (world == 1 and os.environ.get("JSD_OVERLAP", "1") == "0") else 6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

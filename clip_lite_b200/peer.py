@@ -36,6 +36,11 @@ class _DevBuffer:
         _lib.call("jsd_peer_alloc", nbytes, ctypes.byref(ptr))
         self.ptr, self.nbytes = ptr.value, nbytes
 
+    def free(self):
+        if self.ptr:
+            _lib.call("jsd_peer_free", self.ptr)
+            self.ptr = 0
+
     def handle(self) -> bytes:
         buf = ctypes.create_string_buffer(_lib.PEER_HANDLE_BYTES)
         _lib.call("jsd_peer_export", self.ptr, buf)
@@ -95,11 +100,18 @@ class PeerExchange:
         dist.barrier(group=group)          # every rank has mapped every buffer before anyone launches
 
     def close(self):
+        """Collective: unmap the peers' buffers, then free this rank's (nobody may still be reading them)."""
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         for p in self._opened:
             _lib.call("jsd_peer_close", p)
         self._opened = []
+        dist.barrier(group=self.group)
+        self.v_all = []
+        for b in (*self._v, self._stage, self._flags):
+            b.free()
+        for key in [k for k, v in _EXCHANGES.items() if v is self]:
+            del _EXCHANGES[key]
 
     # ------------------------------------------------------------------ the four fused launches
     def normalize_push(self, f: torch.Tensor, g: torch.Tensor, parity: int):

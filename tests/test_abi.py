@@ -71,3 +71,29 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.JSDLibraryError):
         _lib.load()
+
+
+def test_peer_ctx_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of struct jsd_peer_ctx has the size and field offsets the C compiler gives the header's."""
+    import subprocess
+    from clip_lite_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "jsd_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(jsd_peer_ctx), '
+        'offsetof(jsd_peer_ctx, rank), offsetof(jsd_peer_ctx, world), offsetof(jsd_peer_ctx, rows), '
+        'offsetof(jsd_peer_ctx, dim), offsetof(jsd_peer_ctx, v_all), offsetof(jsd_peer_ctx, stage), '
+        'offsetof(jsd_peer_ctx, flags), JSD_MAX_PEERS, JSD_PEER_HANDLE_BYTES); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    c = _lib.PeerCtx
+    want = [ctypes.sizeof(c), c.rank.offset, c.world.offset, c.rows.offset, c.dim.offset, c.v_all.offset,
+            c.stage.offset, c.flags.offset, _lib.MAX_PEERS, _lib.PEER_HANDLE_BYTES]
+    assert got == want
+
+
+def test_header_is_plain_c():
+    """include/jsd_b200.h compiles as C (no C++-isms, no CUDA or torch types in the boundary)."""
+    import subprocess
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", HEADER], check=True)

@@ -155,3 +155,41 @@ def test_zero_shot_argmax_matches_torch_max(n, classes, dim):
     # F.normalize fused into the operand split gives the same prediction from un-normalised features
     _, pred2 = R.score_argmax((3.0 * feats).cuda(), (0.5 * prompts).cuda(), normalize=True)
     assert float((pred2.cpu() != pred).float().mean()) < 0.01
+
+
+# ------------------------------------------------------------------ host logic of the drop-in (CPU tier)
+def test_itm_eval_host_logic_with_oracle_ranks(monkeypatch, golden_dir):
+    """clip_lite_b200.retrieval.itm_eval = id bookkeeping + rank kernel + recall formulae.  With the rank kernel
+    replaced by the oracle's ranks (the CUDA library cannot run here) the bookkeeping and the formulae must
+    reproduce the reference's golden metric dictionaries exactly."""
+    from clip_lite_b200 import retrieval as R
+    seen = {}
+
+    def fake_ranks(image_embeds, text_embeds, row_targets, col_targets, normalize, precision):
+        s = (image_embeds.double() @ text_embeds.double().t()).numpy()
+        seen["rows"], seen["cols"] = row_targets, col_targets
+        r = ro.rank_above(s, row_targets)
+        c = ro.rank_above(s.T, [[int(x)] for x in col_targets])
+        return torch.from_numpy(r), torch.from_numpy(c)
+
+    monkeypatch.setattr(R, "retrieval_ranks", fake_ranks)
+    for path in _cases(golden_dir):
+        img, txt, txt2img, img2txt, ids, want = _load(path)
+        got = R.itm_eval(img, txt, txt2img, img2txt, torch.tensor(ids))
+        assert got.keys() == want.keys()
+        for k in want:
+            assert abs(got[k] - want[k]) < 1e-9, (os.path.basename(path), k)
+        assert len(seen["rows"]) == img.shape[0] and len(seen["cols"]) == txt.shape[0]
+
+
+def test_csr_and_argument_checks():
+    from clip_lite_b200 import retrieval as R
+    ptr, idx = R._csr([[3, 1], [], [2]], "cpu")
+    assert ptr.tolist() == [0, 2, 2, 3] and idx.tolist() == [3, 1, 2]
+    assert ptr.dtype == torch.int32 and idx.dtype == torch.int32
+    with pytest.raises(RuntimeError):                       # CPU tensors are refused: there is no CPU path
+        R.prepare_operand(torch.zeros(4, 8), 0)
+    m = R.recall_metrics(torch.tensor([0, 3, 7, 12]), torch.tensor([0, 0, 5, 9]))
+    assert m["txt_r1"] == 25.0 and m["txt_r5"] == 50.0 and m["txt_r10"] == 75.0
+    assert m["img_r1"] == 50.0 and m["img_r5"] == 50.0 and m["img_r10"] == 100.0
+    assert abs(m["r_mean"] - ((25 + 50 + 75) / 3 + (50 + 50 + 100) / 3) / 2) < 1e-12

@@ -104,6 +104,24 @@ def global_loss_for_logging(local_loss: torch.Tensor, group: Optional[object] = 
     return out
 
 
+def average_loss_components(components, group: Optional[object] = None):
+    """Fused replacement for the reference's ``average_across_processes`` on the loss dictionary
+    (utils/distributed.py:141-159 reduces each of the four 0-dim tensors of model.py:103-111 with its own
+    all-reduce): the values are packed into one vector, reduced by ONE collective and written back in place.
+    Accepts the dictionary of 0-dim tensors (same device) or a single tensor; returns its argument."""
+    _, world = _world(group)
+    single = isinstance(components, torch.Tensor)
+    items = [("", components)] if single else list(components.items())
+    if world > 1 and items:
+        packed = torch.stack([v.detach().reshape(()).float() for _, v in items])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        packed /= world
+        with torch.no_grad():
+            for i, (_, v) in enumerate(items):
+                v.copy_(packed[i].to(v.dtype))
+    return components
+
+
 class GraphedGatheredStep:
     """Forward + backward of the gathered dense loss with the library kernels replayed from CUDA graphs.
 

@@ -88,3 +88,33 @@ def test_single_process_path_needs_no_process_group():
         assert abs(float(t.grad) - float(dt)) < 1e-2 * abs(float(dt))
     finally:
         parallel.K = old
+
+
+def _avg_worker(rank, world, port, results):
+    from clip_lite_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comps = {"total_loss": torch.tensor(1.0 + rank), "cross_modal_loss": torch.tensor(0.5 * (rank + 1)),
+                 "visual_loss": torch.tensor(0.0), "textual_loss": torch.tensor(float(rank) ** 2)}
+        out = parallel.average_loss_components(comps)
+        single = parallel.average_loss_components(torch.tensor(10.0 * rank))
+        results[rank] = ({k: float(v) for k, v in out.items()}, float(single), out is comps)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_average_loss_components_matches_the_reference_semantics():
+    """One packed all-reduce gives what utils/distributed.py:141-159 computes with four: the mean over ranks,
+    written back in place, identical on every rank."""
+    world = 2
+    results = mp.Manager().dict()
+    mp.spawn(_avg_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    want = {"total_loss": 1.5, "cross_modal_loss": 0.75, "visual_loss": 0.0, "textual_loss": 0.5}
+    for r in range(world):
+        got, single, same_object = results[r]
+        assert got == want and single == 5.0 and same_object
+    from clip_lite_b200 import parallel            # without a process group it is the identity
+    d = {"total_loss": torch.tensor(2.0)}
+    assert parallel.average_loss_components(d) is d and float(d["total_loss"]) == 2.0

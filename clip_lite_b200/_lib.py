@@ -68,6 +68,7 @@ SIGNATURES = {
     "jsd_score_ranks": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_score_argmax": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "jsd_trace_enable": (c_int, [c_void_p, c_int, c_void_p]),
     "jsd_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64,
                               c_void_p, c_void_p, c_void_p]),
 }

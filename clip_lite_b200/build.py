@@ -32,8 +32,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into csrc/libjsd_b200.so; returns the library path."""
+TRACE_LIB_PATH = os.path.join(CSRC, "libjsd_b200_trace.so")
+
+
+def build_library(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/libjsd_b200.so; returns the library path.  trace=True builds the instrumented
+    variant libjsd_b200_trace.so (-DJSD_TRACE=1, see clip_lite_b200/trace.py; select it with JSD_LIB=...)."""
+    if trace:
+        cmd = [_nvcc(), *NVCC_FLAGS, "-DJSD_TRACE=1", "-o", TRACE_LIB_PATH] + SOURCES
+        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return TRACE_LIB_PATH
     if not force and not is_stale():
         return LIB_PATH
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + SOURCES

@@ -835,6 +835,24 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
   return 0;
 }
 
+/* ------------------------------------------------------------------ device-side event trace */
+int jsd_trace_enable(unsigned long long* events, int capacity, int* count) {
+#if !JSD_TRACE
+  (void)events;
+  (void)capacity;
+  (void)count;
+  return fail("this libjsd_b200.so was built without -DJSD_TRACE=1 (build.build_library(trace=True))");
+#else
+  JSD_REQUIRE((events == nullptr) || (count != nullptr && capacity > 0), "jsd_trace_enable: bad argument");
+  jsd::TraceBuf tb;
+  tb.events = events;
+  tb.count = events ? count : nullptr;
+  tb.capacity = events ? capacity : 0;
+  JSD_CUDA_OK(cudaMemcpyToSymbol(jsd::g_trace, &tb, sizeof(tb)));
+  return 0;
+#endif
+}
+
 /* ------------------------------------------------------------------ retrieval / zero-shot scoring */
 int jsd_split_bf16x3(const void* X, int dtype, int64_t rows, int64_t D, int side, int normalize, void* out,
                      jsd_stream_t stream) {

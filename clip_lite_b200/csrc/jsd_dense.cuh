@@ -291,6 +291,8 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_k = (p.K + CHUNK_K - 1) / CHUNK_K;
   const bool stream_k = (MODE == MODE_GRAD) && p.stream_k != 0;
 
+  constexpr int TRACE_ID = MODE == MODE_FWD ? TK_FWD : (MODE == MODE_GRAD ? TK_GRAD : TK_SCORE);
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(TRACE_ID, TE_START);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -345,6 +347,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // the B operand was gathered by peer GPUs writing into this GPU's memory: wait for their "rows are in" flags
         wait_flags_sys(p.wait_flags, p.wait_count, *p.wait_counter);
         fence_proxy_async_all();
+        if (blockIdx.x == 0) trace_event(TRACE_ID, TE_PEERS_IN);
       }
       SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
       int tile, k0, k1;
@@ -779,6 +782,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 
+  if constexpr (MODE != MODE_FWD) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(TRACE_ID, TE_END);   // block 0's end (no last-CTA ticket here)
+  }
   if constexpr (MODE == MODE_GRAD) {
     // Peer exchange: once every CTA's stores are fenced, the last CTA publishes "this rank's partial is complete".
     if (p.peer_world > 0) {
@@ -839,6 +845,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         p.out4[3] = 0.f;
         if (p.loss_out) *p.loss_out = (float)(pos + neg);
         *p.ticket = 0;                                  // re-armed for the next launch on this stream
+        trace_event(TRACE_ID, TE_END);
       }
     }
   }

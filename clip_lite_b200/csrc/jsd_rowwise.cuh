@@ -369,6 +369,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 normalize_push_kernel(const PeerPushJob job, int rows, int D) {
   const int jy = blockIdx.y;
+  if (blockIdx.x == 0 && jy == 0 && threadIdx.x == 0) trace_event(TK_PUSH, TE_START);
   const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -411,6 +412,7 @@ normalize_push_kernel(const PeerPushJob job, int rows, int D) {
     *job.counter = e;
     for (int q = 0; q < job.world; ++q) st_release_sys(job.flag_dst[q], e);
     *job.ticket = 0;
+    trace_event(TK_PUSH, TE_END);
   }
 }
 
@@ -486,8 +488,12 @@ struct NormBwdJob {
 };
 
 __device__ __forceinline__ void normbwd_wait_peers(const NormBwdJob& job) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) trace_event(TK_JACOBIAN, TE_START);
   if (job.wait_flags == nullptr) return;
-  if (threadIdx.x == 0) wait_flags_sys(job.wait_flags, job.wait_count, *job.wait_counter);
+  if (threadIdx.x == 0) {
+    wait_flags_sys(job.wait_flags, job.wait_count, *job.wait_counter);
+    if (blockIdx.x == 0 && blockIdx.y == 0) trace_event(TK_JACOBIAN, TE_PEERS_IN);
+  }
   __syncthreads();
 }
 
@@ -566,6 +572,7 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   }  // row < rows
   if (job.dt_out != nullptr) reduce_rowdot_last_block(job.rowdot, rows, job.ticket, job.dt_out);
   if (job.reduce_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0) block_reduce_to(job.reduce_src, job.reduce_n, job.reduce_out);
+  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x == 0) trace_event(TK_JACOBIAN, TE_END);
 }
 
 // ------------------------------------------------------------------ register-resident variants (D = nch * 128 <= 1024)
@@ -683,6 +690,7 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
   }  // row < rows
   if (job.dt_out != nullptr) reduce_rowdot_last_block(job.rowdot, rows, job.ticket, job.dt_out);
   if (job.reduce_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0) block_reduce_to(job.reduce_src, job.reduce_n, job.reduce_out);
+  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x == 0) trace_event(TK_JACOBIAN, TE_END);
 }
 
 }  // namespace jsd

@@ -93,6 +93,39 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---------------------------------------------------------------- device-side event trace (development aid)
+// nsys is not available on the GPU boxes and ncu serialises launches, so the kernels can stamp %globaltimer into a
+// caller-provided buffer: one thread per kernel at entry / once its peers' flags are in / at exit.  Disabled
+// (events == nullptr, the default) it costs one 8-byte load in that one thread.  See clip_lite_b200/trace.py.
+// Compiled in only with -DJSD_TRACE=1 (clip_lite_b200.build.build_library(trace=True) -> libjsd_b200_trace.so); the
+// default build contains no trace code at all.
+#ifndef JSD_TRACE
+#define JSD_TRACE 0
+#endif
+struct TraceBuf {
+  unsigned long long* events;   // [capacity]: (kernel id << 60) | (event << 56) | (globaltimer ns & (2^56 - 1))
+  int* count;                   // next free slot
+  int capacity;
+};
+#if JSD_TRACE
+__device__ TraceBuf g_trace = {nullptr, nullptr, 0};
+#endif
+enum TraceKernel { TK_NORMALIZE = 1, TK_FWD = 2, TK_GRAD = 3, TK_JACOBIAN = 4, TK_INDEX = 5, TK_SCORE = 6, TK_PUSH = 7 };
+enum TraceEvent { TE_START = 0, TE_PEERS_IN = 1, TE_END = 2 };
+__device__ __forceinline__ void trace_event(int kernel, int event) {
+#if JSD_TRACE
+  unsigned long long* ev = g_trace.events;
+  if (ev == nullptr) return;
+  const int i = atomicAdd(g_trace.count, 1);
+  if (i < g_trace.capacity)
+    ev[i] = ((unsigned long long)kernel << 60) | ((unsigned long long)event << 56) |
+            (global_timer_ns() & ((1ull << 56) - 1));
+#else
+  (void)kernel;
+  (void)event;
+#endif
+}
+
 // ---------------------------------------------------------------- system-scope flags (peer GPUs over NVLink)
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;

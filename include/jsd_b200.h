@@ -240,6 +240,14 @@ int jsd_score_ranks(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N
 int jsd_score_argmax(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, unsigned long long* best,
                      jsd_stream_t stream);
 
+/* Development aid: device-side event trace.  With a buffer installed (events != NULL; *count zeroed by the caller),
+ * one thread of every kernel appends (kernel id << 60 | event << 56 | %globaltimer ns) at entry (event 0), once the
+ * flags of its peers are in (1, peer-exchange consumers only) and at exit (2).  Kernel ids: 1 normalise, 2 forward
+ * GEMM, 3 backward GEMM, 4 Jacobian, 5 index, 6 score, 7 normalise + push.  events == NULL switches it off (the
+ * default; the cost is one load in one thread per launch).  Synchronous (cudaMemcpyToSymbol); affects the current
+ * device only; not for use during a CUDA-graph capture. */
+int jsd_trace_enable(unsigned long long* events, int capacity, int* count);
+
 /* Plain C [M, N] fp32 = A . B^T on the same tcgen05 kernel, every operand-layout combination:
  * A [M, K] bf16 (a_mn_major = 0) or A^T [K, lda] (a_mn_major = 1); B [N, K] (b_mn_major = 0) or
  * B^T [K, ldb] (b_mn_major = 1).  sk_workspace as above (NULL => whole tiles only).

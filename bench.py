@@ -231,9 +231,9 @@ def run_b200(args, wl):
 
     def loss_fn(f, g):
         if exchange == "peer":
-            return peer.peer_dense_loss(f, g, t_dev)[0]
+            return peer.peer_dense_loss(f, g, t_dev, route=args.route)[0]
         if world > 1:
-            return parallel.gathered_dense_loss(f, g, t_dev)[0]
+            return parallel.gathered_dense_loss(f, g, t_dev, route=args.route)[0]
         return ops.jsd_dense_loss(f, g, t_dev)[0]
 
     def eager_step():
@@ -249,7 +249,9 @@ def run_b200(args, wl):
                 from clip_lite_b200.graph import GraphedStep
                 gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
             elif exchange == "peer":   # no collective call in the step: one graph launch per step
-                gs = peer.PeerGraphedStep(f_dev, g_dev, t_dev)
+                gs = peer.PeerGraphedStep(f_dev, g_dev, t_dev, route=args.route)
+            elif args.route != "reduce":
+                raise RuntimeError("the segmented graph step of the NCCL exchange implements the reduce route only")
             else:      # NCCL is not captured: graph segments between the two eagerly launched collectives
                 gs = parallel.GraphedGatheredStep(f_dev, g_dev, t_dev)
             step, graphed = gs, True
@@ -432,6 +434,7 @@ def run_b200(args, wl):
             "data": "synthetic",
             "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "rows_per_gpu": rows,
                        "neg_mode": "dense", "parallelism": f"dp{world}", "cuda_graph": graphed, "exchange": exchange,
+                       "route": args.route if world > 1 else "none",
                        "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
                        "inputs": "bf16 unit rows resident in HBM; N(0,1) features, text = 0.6 img + 0.8 noise"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
@@ -458,6 +461,9 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="dense_b8192_d1024")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the step as one CUDA graph (default 1)")
+    ap.add_argument("--route", choices=["reduce", "symmetric"], default="reduce",
+                    help="N > 1: text-side gradient by reducing the ranks' partials (measured default) or by also "
+                         "exchanging the image rows and recomputing the owned column slab (no gradient traffic)")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N > 1: exchange fused into the kernels over NVLink peer memory, or NCCL collectives")
     args = ap.parse_args()

@@ -40,9 +40,12 @@ def _all_gather_rows(x: torch.Tensor, world: int, group) -> torch.Tensor:
     return out
 
 
+ROUTES = ("reduce", "symmetric")
+
+
 class _GatheredDenseFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, f, g, t, group):
+    def forward(ctx, f, g, t, group, route="reduce"):
         rank, world = _world(group)
         need_grad = any(ctx.needs_input_grad)
         if f.dim() != 2 or f.shape != g.shape:
@@ -56,7 +59,7 @@ class _GatheredDenseFn(torch.autograd.Function):
             out4, loss, gmat, gdiag = K.dense_fwd(u, v_all, t, row_offset=rank * m, want_grad=need_grad)
         if need_grad:
             ctx.save_for_backward(fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag)
-        ctx.group, ctx.rank, ctx.world = group, rank, world
+        ctx.group, ctx.rank, ctx.world, ctx.route = group, rank, world, route
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         ctx.mark_non_differentiable(out4)
         return loss, out4
@@ -65,6 +68,8 @@ class _GatheredDenseFn(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_stats):
         fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag = ctx.saved_tensors
         m, n = fc.shape[0], v_all.shape[0]
+        if ctx.route == "symmetric" and ctx.world > 1:
+            return _GatheredDenseFn._backward_symmetric(ctx, grad_loss)
         with torch.autocast(fc.device.type, enabled=False):
             gamma = grad_loss.float()
             # text side first: its reduce-scatter runs on NCCL's stream while the image side computes
@@ -82,16 +87,44 @@ class _GatheredDenseFn(torch.autograd.Function):
                 work.wait()                                                    # compute stream waits for the reduction
             dg = K.normalize_bwd(gc, inv_g, dv, u, 0, gdiag, t, gamma, m)
         fd, gd, td = ctx.dtypes
-        return df.to(fd), dg.to(gd), dt.to(td), None
+        return df.to(fd), dg.to(gd), dt.to(td), None, None
+
+    @staticmethod
+    def _backward_symmetric(ctx, grad_loss):
+        """No gradient traffic: the image rows are gathered as well and this rank recomputes the COLUMN slab it
+        owns, sigma(tau V_r U_all^T) = (G[:, own columns])^T, with the forward kernel (roles of the two modalities
+        swapped, same row offset); dV_r = scale G[:, own]^T U_all is then the image-side backward with the roles
+        swapped.  Costs one more slab forward, saves the reduce-scatter of a [B, D] fp32 partial."""
+        fc, gc, t, u, v_all, inv_f, inv_g, gmat, gdiag = ctx.saved_tensors
+        m = fc.shape[0]
+        off = ctx.rank * m
+        with torch.autocast(fc.device.type, enabled=False):
+            gamma = grad_loss.float()
+            u_all = _all_gather_rows(u, ctx.world, ctx.group)
+            df, dt = K.dense_backward_image_side(fc, v_all, inv_f, gmat, gdiag, t, gamma, off)
+            v = v_all[off:off + m]
+            _, _, gmat_t, gdiag_t = K.dense_fwd(v, u_all, t, row_offset=off, want_grad=True)
+            dg, _ = K.dense_backward_image_side(gc, u_all, inv_g, gmat_t, gdiag_t, t, gamma, off)
+        fd, gd, td = ctx.dtypes
+        return df.to(fd), dg.to(gd), dt.to(td), None, None
 
 
-def gathered_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group: Optional[object] = None):
+def gathered_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group: Optional[object] = None,
+                        route: str = "reduce"):
     """(L_r, stats) for this rank's rows against the all-gathered text batch.
-    f, g: [B_local, D] projected features (same B_local on every rank)."""
+    f, g: [B_local, D] projected features (same B_local on every rank).
+
+    route  how the text-side gradient is completed across ranks:
+           "reduce"     every rank's partial over all text rows is reduce-scattered (sum) to the owners;
+           "symmetric"  the image rows are all-gathered too and every rank recomputes its own column slab: one
+                        more slab forward, no gradient traffic, a single exchange phase per step.  Requires the
+                        same upstream gradient d(total)/d(L_r) on every rank (true under DDP / GradScaler)."""
+    if route not in ROUTES:
+        raise ValueError(f"route must be one of {ROUTES}, got {route!r}")
     _, world = _world(group)
     if world * f.shape[0] < 2:
         raise ValueError("the dense estimator needs at least two rows in the global batch")
-    return _GatheredDenseFn.apply(f, g, t, group)
+    return _GatheredDenseFn.apply(f, g, t, group, route)
 
 
 def global_loss_for_logging(local_loss: torch.Tensor, group: Optional[object] = None) -> torch.Tensor:

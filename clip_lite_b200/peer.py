@@ -170,9 +170,10 @@ class PeerExchange:
 _EXCHANGES = {}
 
 
-def get_exchange(rows: int, dim: int, group=None) -> PeerExchange:
-    """Cached PeerExchange per (group, rows, D); the first call is collective."""
-    key = (id(group) if group is not None else 0, rows, dim, torch.cuda.current_device())
+def get_exchange(rows: int, dim: int, group=None, tag: str = "text") -> PeerExchange:
+    """Cached PeerExchange per (group, rows, D, tag); the first call is collective.  ``tag`` names independent
+    exchanges of the same shape (the symmetric route gathers the image rows through a second one)."""
+    key = (id(group) if group is not None else 0, rows, dim, torch.cuda.current_device(), tag)
     ex = _EXCHANGES.get(key)
     if ex is None:
         ex = _EXCHANGES[key] = PeerExchange(rows, dim, group)
@@ -212,9 +213,64 @@ class _PeerDenseFn(torch.autograd.Function):
         return df.to(fd), dg.to(gd), dt.to(td), None
 
 
+class _PeerSymmetricFn(torch.autograd.Function):
+    """Peer route without gradient traffic (see parallel.gathered_dense_loss, route="symmetric"): the text rows AND
+    the image rows are pushed into every rank's gathered buffers (two exchanges), the forward computes this rank's
+    row slab sigma(tau U_r V_all^T) and its column slab sigma(tau V_r U_all^T) (the same kernel with the roles of
+    the modalities swapped), and the backward is two purely local image-side backwards.  All waiting on peers
+    happens in the forward; nothing is pulled or reduced afterwards.  Built from the entry points the "reduce"
+    route uses -- not yet timed on hardware (written after the round's GPU budget was spent)."""
+
+    @staticmethod
+    def forward(ctx, f, g, t, ex_v: PeerExchange, ex_u: PeerExchange):
+        need_grad = any(ctx.needs_input_grad)
+        with torch.autocast(f.device.type, enabled=False):
+            dt = torch.promote_types(f.dtype, g.dtype)
+            fc, gc = f.to(dt).contiguous(), g.to(dt).contiguous()
+            parity = ex_v.step & 1
+            ex_v.step += 1
+            ex_u.step = ex_v.step
+            # both pushes always happen (collective semantics must not depend on who needs gradients)
+            u, inv_f, inv_g = ex_v.normalize_push(fc, gc, parity)      # U local, text rows -> every rank
+            v, _, _ = ex_u.normalize_push(gc, fc, parity)              # V local, image rows -> every rank
+            out4, loss, gmat, gdiag = ex_v.dense_fwd(u, t, parity, want_grad=need_grad)
+            gmat_t = gdiag_t = None
+            if need_grad:
+                _, _, gmat_t, gdiag_t = ex_u.dense_fwd(v, t, parity, want_grad=True)
+        if need_grad:
+            ctx.save_for_backward(fc, gc, t, inv_f, inv_g, gmat, gdiag, gmat_t, gdiag_t)
+        ctx.ex_v, ctx.ex_u, ctx.parity, ctx.step = ex_v, ex_u, parity, ex_v.step
+        ctx.dtypes = (f.dtype, g.dtype, t.dtype)
+        ctx.mark_non_differentiable(out4)
+        return loss, out4
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        ex_v, ex_u = ctx.ex_v, ctx.ex_u
+        if ex_v.step != ctx.step:
+            raise RuntimeError("peer exchange: backward of a step after a newer forward (one step in flight at a time)")
+        fc, gc, t, inv_f, inv_g, gmat, gdiag, gmat_t, gdiag_t = ctx.saved_tensors
+        off = ex_v.rank * ex_v.rows
+        with torch.autocast(fc.device.type, enabled=False):
+            gamma = grad_loss.float()
+            df, dt = K.dense_backward_image_side(fc, ex_v.v_all[ctx.parity], inv_f, gmat, gdiag, t, gamma, off)
+            dg, _ = K.dense_backward_image_side(gc, ex_u.v_all[ctx.parity], inv_g, gmat_t, gdiag_t, t, gamma, off)
+        fd, gd, td = ctx.dtypes
+        return df.to(fd), dg.to(gd), dt.to(td), None, None
+
+
 def peer_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group=None,
-                    exchange: Optional[PeerExchange] = None):
-    """(L_r, stats) for this rank's rows against the text rows of every rank, exchanged over peer memory."""
+                    exchange: Optional[PeerExchange] = None, route: str = "reduce"):
+    """(L_r, stats) for this rank's rows against the text rows of every rank, exchanged over peer memory.
+    route="reduce" (default, measured): dV partials are pulled and summed by the owners; route="symmetric": the
+    image rows are exchanged as well and every rank recomputes its own column slab (no gradient traffic; needs
+    the same upstream gradient on every rank)."""
+    if route == "symmetric":
+        ex_v = exchange if exchange is not None else get_exchange(f.shape[0], f.shape[1], group)
+        ex_u = get_exchange(f.shape[0], f.shape[1], group, tag="image")
+        return _PeerSymmetricFn.apply(f, g, t, ex_v, ex_u)
+    if route != "reduce":
+        raise ValueError(f"route must be 'reduce' or 'symmetric', got {route!r}")
     ex = exchange if exchange is not None else get_exchange(f.shape[0], f.shape[1], group)
     return _PeerDenseFn.apply(f, g, t, ex)
 
@@ -224,19 +280,36 @@ class PeerGraphedStep:
     is no collective call to keep outside the graph).  Two graphs are captured, one per parity of the
     double-buffered gathered V, and replayed alternately.  Returns static tensors (loss, dF, dG, dt)."""
 
-    def __init__(self, f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group=None, warmup: int = 2):
+    def __init__(self, f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group=None, warmup: int = 2,
+                 route: str = "reduce"):
+        if route not in ("reduce", "symmetric"):
+            raise ValueError(f"route must be 'reduce' or 'symmetric', got {route!r}")
         self.ex = get_exchange(f.shape[0], f.shape[1], group)
+        ex_u = get_exchange(f.shape[0], f.shape[1], group, tag="image") if route == "symmetric" else None
         self.f = f.detach().clone()
         self.g = g.detach().clone()
         self.t = t.detach()
         self.gamma = torch.ones((), dtype=torch.float32, device=f.device)
         ex = self.ex
 
-        def step(parity):
+        def step_reduce(parity):
             u, inv_f, inv_g = ex.normalize_push(self.f, self.g, parity)
             out4, loss, gmat, gdiag = ex.dense_fwd(u, self.t, parity)
             df, dg, dt = ex.dense_backward(self.f, self.g, self.t, self.gamma, parity, u, inv_f, inv_g, gmat, gdiag)
             return loss, df, dg, dt
+
+        def step_symmetric(parity):
+            off = ex.rank * ex.rows
+            u, inv_f, inv_g = ex.normalize_push(self.f, self.g, parity)
+            v, _, _ = ex_u.normalize_push(self.g, self.f, parity)
+            out4, loss, gmat, gdiag = ex.dense_fwd(u, self.t, parity)
+            _, _, gmat_t, gdiag_t = ex_u.dense_fwd(v, self.t, parity)
+            df, dt = K.dense_backward_image_side(self.f, ex.v_all[parity], inv_f, gmat, gdiag, self.t, self.gamma, off)
+            dg, _ = K.dense_backward_image_side(self.g, ex_u.v_all[parity], inv_g, gmat_t, gdiag_t, self.t,
+                                                self.gamma, off)
+            return loss, df, dg, dt
+
+        step = step_symmetric if route == "symmetric" else step_reduce
 
         p0 = ex.step & 1                   # pushes below come in (p0, p0 ^ 1) pairs: the exchange's parity is kept
         side = torch.cuda.Stream(device=f.device)

@@ -132,3 +132,74 @@ def test_peer_exchange_matches_single_gpu(world):
     for r in range(world):      # graph replay == eager on the same data (deterministic kernels, fixed slot order)
         for a, b in zip(results[r][2], results[r][3]):
             assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ "symmetric" route (no gradient traffic)
+# Host logic validated on CPU (tests/test_parallel_cpu.py, gloo, world 2 and 4); the kernels are the ones the
+# "reduce" route uses.  Written after the round's GPU budget was spent, so these multi-GPU checks are opt-in until
+# their first run: JSD_TEST_SYMMETRIC=1 python -m pytest tests/test_gpu_parallel.py -m gpu -k symmetric
+_SYMMETRIC = pytest.mark.skipif(os.environ.get("JSD_TEST_SYMMETRIC") != "1",
+                                reason="symmetric route not yet exercised on hardware (set JSD_TEST_SYMMETRIC=1)")
+
+
+def _symmetric_worker(rank, world, port, results, use_peer):
+    from clip_lite_b200 import parallel, peer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m = B // world
+        t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
+        out = []
+        for seed in (0, 1, 2):
+            f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+            fl = f[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
+            gl = g[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
+            t.grad = None
+            if use_peer:
+                loss, _ = peer.peer_dense_loss(fl, gl, t, route="symmetric")
+            else:
+                loss, _ = parallel.gathered_dense_loss(fl, gl, t, route="symmetric")
+            (0.5 * loss).backward()
+            torch.cuda.synchronize()
+            out.append(tuple(x.detach().cpu() for x in (loss, fl.grad, gl.grad, t.grad)))
+        if use_peer:
+            gs = peer.PeerGraphedStep(fl.detach(), gl.detach(), t.detach(), route="symmetric")
+            gs.gamma.fill_(0.5)
+            for _ in range(5):
+                l2, df2, dg2, dt2 = gs()
+            torch.cuda.synchronize()
+            out.append(tuple(x.detach().cpu().clone() for x in (l2, df2, dg2, dt2)))
+        results[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@_SYMMETRIC
+@pytest.mark.parametrize("use_peer", [False, True])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_symmetric_route_matches_single_gpu(world, use_peer):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_symmetric_worker, args=(world, _free_port(), results, use_peer), nprocs=world, join=True)
+    m = B // world
+    for si, seed in enumerate((0, 1, 2)):
+        f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+        fd, gd = f.double(), g.double()
+        df, dg, dt = orc.jsd_dense_grads(fd, gd, orc.T_INIT, gamma=0.5)
+        tot_dt = 0.0
+        for r in range(world):
+            loss, gf, gg, gt = results[r][si]
+            slab = orc.jsd_dense(fd[r * m:(r + 1) * m], gd, orc.T_INIT, row_offset=r * m)
+            assert abs(float(loss) - float(slab["loss"])) < 1e-3 * float(slab["loss"])
+            ref_f, ref_g = world * df[r * m:(r + 1) * m], world * dg[r * m:(r + 1) * m]
+            assert (gf.double() - ref_f).abs().max() < 1e-2 * ref_f.abs().max()
+            assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
+            tot_dt += float(gt)
+        assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
+    if use_peer:
+        for r in range(world):
+            for a, b in zip(results[r][2], results[r][3]):
+                assert torch.equal(a, b)

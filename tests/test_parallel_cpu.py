@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, results):
+def _worker(rank, world, port, results, route="reduce"):
     from tests import _standin_kernels
     from clip_lite_b200 import parallel
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -35,7 +35,7 @@ def _worker(rank, world, port, results):
         fl = f[rank * m:(rank + 1) * m].clone().requires_grad_(True)
         gl = g[rank * m:(rank + 1) * m].clone().requires_grad_(True)
         t = torch.tensor(T, requires_grad=True)
-        loss, stats = parallel.gathered_dense_loss(fl, gl, t)
+        loss, stats = parallel.gathered_dense_loss(fl, gl, t, route=route)
         (0.5 * loss).backward()
         logged = parallel.global_loss_for_logging(loss)
         results[rank] = (loss.detach(), fl.grad, gl.grad, t.grad, logged, stats)
@@ -43,11 +43,13 @@ def _worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_gathered_dense_equals_single_process_dense(world):
+@pytest.mark.parametrize("world,route", [(2, "reduce"), (2, "symmetric"), (4, "symmetric")])
+def test_gathered_dense_equals_single_process_dense(world, route):
+    """Both ways of completing the text-side gradient across ranks -- reduce-scatter of the partials, or gathering
+    the image rows as well and recomputing the owned column slab -- give the single-process dense gradients."""
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), results, route), nprocs=world, join=True)
     f, g = orc.synth_embeddings(B, D, seed=0, correlated=True)
     fd, gd = f.double(), g.double()
     full = orc.jsd_dense(fd, gd, T)
@@ -118,3 +120,9 @@ def test_average_loss_components_matches_the_reference_semantics():
     from clip_lite_b200 import parallel            # without a process group it is the identity
     d = {"total_loss": torch.tensor(2.0)}
     assert parallel.average_loss_components(d) is d and float(d["total_loss"]) == 2.0
+
+
+def test_unknown_route_is_refused():
+    from clip_lite_b200 import parallel
+    with pytest.raises(ValueError):
+        parallel.gathered_dense_loss(torch.zeros(4, 8), torch.zeros(4, 8), torch.tensor(0.0), route="ring")

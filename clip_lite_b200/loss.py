@@ -154,6 +154,9 @@ class JSDInfoMaxLoss(nn.Module):
                 scatter collectives, any process group) or "peer" (both exchanges fused
                 into the kernels over NVLink peer memory; <= 8 GPUs of one node, fixed
                 per-rank batch size -- see clip_lite_b200.peer).
+      route     how ``gather`` completes the text-side gradient: "reduce" (default: the ranks'
+                partials are summed on the owning rank) or "symmetric" (the image embeddings are
+                exchanged as well and each rank recomputes its own column slab: no gradient traffic).
     """
 
     def __init__(
@@ -171,6 +174,7 @@ class JSDInfoMaxLoss(nn.Module):
         gather: bool = False,
         process_group=None,
         exchange: str = "nccl",
+        route: str = "reduce",
     ):
         super().__init__()
         if type not in _DOT_TYPES + _CONCAT_TYPES:
@@ -181,6 +185,8 @@ class JSDInfoMaxLoss(nn.Module):
             raise ValueError("gather=True requires neg_mode='dense'")
         if exchange not in ("nccl", "peer"):
             raise ValueError(f"exchange must be 'nccl' or 'peer', got {exchange!r}")
+        if route not in ("reduce", "symmetric"):
+            raise ValueError(f"route must be 'reduce' or 'symmetric', got {route!r}")
         if neg_mode == "dense" and type not in _DOT_TYPES:
             raise ValueError("neg_mode='dense' needs the dot critic (type='dot' or 'dotcon')")
         self.prior_weight = prior_weight
@@ -190,6 +196,7 @@ class JSDInfoMaxLoss(nn.Module):
         self.gather = gather
         self.process_group = process_group
         self.exchange = exchange
+        self.route = route
 
         self.global_d = (GlobalDiscriminatorDot(image_sz=image_dim, text_sz=text_dim) if type in _DOT_TYPES
                          else GlobalDiscriminator(sz=image_dim + text_dim))
@@ -235,10 +242,11 @@ class JSDInfoMaxLoss(nn.Module):
             if allow_dense and self.neg_mode == "dense":
                 if self.gather and self.exchange == "peer":
                     from . import peer
-                    loss, _ = peer.peer_dense_loss(f, g, critic.temperature, self.process_group)
+                    loss, _ = peer.peer_dense_loss(f, g, critic.temperature, self.process_group, route=self.route)
                 elif self.gather:
                     from . import parallel
-                    loss, _ = parallel.gathered_dense_loss(f, g, critic.temperature, self.process_group)
+                    loss, _ = parallel.gathered_dense_loss(f, g, critic.temperature, self.process_group,
+                                                           route=self.route)
                 else:
                     loss, _ = ops.jsd_dense_loss(f, g, critic.temperature)
             else:

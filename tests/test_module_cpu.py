@@ -62,6 +62,14 @@ def test_bad_options_raise():
         L.JSDInfoMaxLoss(image_dim=8, text_dim=8, gather=True)           # gather needs dense
     with pytest.raises(ValueError):
         L.JSDInfoMaxLoss(image_dim=8, text_dim=8, type="concat", neg_mode="dense")
+    with pytest.raises(ValueError):
+        L.JSDInfoMaxLoss(image_dim=8, text_dim=8, neg_mode="dense", gather=True, exchange="mpi")
+    with pytest.raises(ValueError):
+        L.JSDInfoMaxLoss(image_dim=8, text_dim=8, neg_mode="dense", gather=True, route="ring")
+    m = L.JSDInfoMaxLoss(image_dim=8, text_dim=8, neg_mode="dense", gather=True, exchange="peer", route="symmetric")
+    assert (m.exchange, m.route) == ("peer", "symmetric")
+    d = L.JSDInfoMaxLoss(image_dim=8, text_dim=8)
+    assert (d.exchange, d.route) == ("nccl", "reduce")                  # collectives + reduce unless asked otherwise
 
 
 def test_forward_without_cuda_fails_loudly():

@@ -127,10 +127,14 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
                 cudaStream_t st, int sk_policy = SK_RAGGED) {
   auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN, CG>;
   constexpr int smem = jsd::gemm_smem_bytes(CG, MODE);
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it once per device
+  // (a process normally drives one GPU, but nothing here may assume so)
+  static unsigned long long configured_mask = 0;
+  int dev = 0;
+  JSD_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !((configured_mask >> dev) & 1ull)) {
     JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured_mask |= 1ull << dev;
   }
   const int sms = sm_count_cached();
   JSD_REQUIRE(sms >= CG, "no CUDA device");

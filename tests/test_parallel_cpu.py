@@ -126,3 +126,105 @@ def test_unknown_route_is_refused():
     from clip_lite_b200 import parallel
     with pytest.raises(ValueError):
         parallel.gathered_dense_loss(torch.zeros(4, 8), torch.zeros(4, 8), torch.tensor(0.0), route="ring")
+
+
+# ------------------------------------------------------------------ peer route: autograd wiring on CPU
+class _FakeExchange:
+    """CPU stand-in for clip_lite_b200.peer.PeerExchange: the same four-method surface the autograd functions
+    use, with the push replaced by a gloo all-gather and the kernels by the oracle-backed stand-ins.  It lets the
+    WIRING of the peer routes (argument order, role swapping, row offsets, what is saved for backward, the
+    gradient convention) be checked without CUDA IPC; the flag protocol itself is covered by the multi-GPU tests."""
+
+    def __init__(self, rows, dim):
+        from tests import _standin_kernels as SK
+        self.SK = SK
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rows, self.dim, self.step = rows, dim, 0
+        self.v_all = [None, None]
+        self.pushes = 0
+
+    def normalize_push(self, f, g, parity):
+        u, inv_f = self.SK.normalize_cast(f)
+        v, inv_g = self.SK.normalize_cast(g)
+        out = torch.empty(self.world * self.rows, self.dim, dtype=v.dtype)
+        dist.all_gather_into_tensor(out, v.contiguous())
+        self.v_all[parity] = out
+        self.pushes += 1
+        return u, inv_f, inv_g
+
+    def dense_fwd(self, u, t, parity, want_grad=True):
+        return self.SK.dense_fwd(u, self.v_all[parity], t, row_offset=self.rank * self.rows, want_grad=want_grad)
+
+    def dense_backward(self, f, g, t, gamma, parity, u, inv_f, inv_g, gmat, gdiag):
+        """What jsd_peer_dense_backward does: dV partial over all text rows, summed across ranks on the owner."""
+        n, m, off = self.world * self.rows, self.rows, self.rank * self.rows
+        part = self.SK.dense_bwd_dv(gmat, u, n, t, gamma)
+        dv = self._sum_rows(part)[off:off + m].contiguous()       # gloo has no reduce-scatter: all-reduce + slice
+        df, dt = self.SK.dense_backward_image_side(f, self.v_all[parity], inv_f, gmat, gdiag, t, gamma, off)
+        dg = self.SK.normalize_bwd(g, inv_g, dv, u, 0, gdiag, t, gamma, m)
+        return df, dg, dt
+
+    @staticmethod
+    def _sum_rows(part):
+        tot = part.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        return tot
+
+
+def _peer_wiring_worker(rank, world, port, results, route):
+    from tests import _standin_kernels
+    from clip_lite_b200 import peer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        peer.K = _standin_kernels
+        m = B // world
+        ex_v, ex_u = _FakeExchange(m, D), _FakeExchange(m, D)
+        out = []
+        for seed in (0, 1):                      # two steps: both parities
+            f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+            fl = f[rank * m:(rank + 1) * m].clone().requires_grad_(True)
+            gl = g[rank * m:(rank + 1) * m].clone().requires_grad_(True)
+            t = torch.tensor(T, requires_grad=True)
+            if route == "symmetric":
+                loss, stats = peer._PeerSymmetricFn.apply(fl, gl, t, ex_v, ex_u)
+            else:
+                loss, stats = peer._PeerDenseFn.apply(fl, gl, t, ex_v)
+            (0.5 * loss).backward()
+            out.append((loss.detach(), fl.grad, gl.grad, t.grad))
+        with torch.no_grad():                    # forward only: both pushes still happen on the symmetric route
+            before = (ex_v.pushes, ex_u.pushes)
+            if route == "symmetric":
+                peer._PeerSymmetricFn.apply(fl.detach(), gl.detach(), t.detach(), ex_v, ex_u)
+            else:
+                peer._PeerDenseFn.apply(fl.detach(), gl.detach(), t.detach(), ex_v)
+            pushes = (ex_v.pushes - before[0], ex_u.pushes - before[1])
+        results[rank] = (out, pushes, ex_v.step)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,route", [(2, "reduce"), (2, "symmetric"), (4, "symmetric")])
+def test_peer_autograd_wiring_matches_single_process_dense(world, route):
+    results = mp.Manager().dict()
+    mp.spawn(_peer_wiring_worker, args=(world, _free_port(), results, route), nprocs=world, join=True)
+    m = B // world
+    for si, seed in enumerate((0, 1)):
+        f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+        fd, gd = f.double(), g.double()
+        df, dg, dt = orc.jsd_dense_grads(fd, gd, T, gamma=0.5)
+        tot_dt = 0.0
+        for r in range(world):
+            loss, gf, gg, gt = results[r][0][si]
+            slab = orc.jsd_dense(fd[r * m:(r + 1) * m], gd, T, row_offset=r * m)
+            assert abs(float(loss) - float(slab["loss"])) < 1e-3 * float(slab["loss"])
+            ref_f, ref_g = world * df[r * m:(r + 1) * m], world * dg[r * m:(r + 1) * m]
+            assert (gf.double() - ref_f).abs().max() < 1e-2 * ref_f.abs().max()
+            assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
+            tot_dt += float(gt)
+        assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
+    for r in range(world):
+        _, pushes, steps = results[r]
+        assert pushes == ((1, 1) if route == "symmetric" else (1, 0))
+        assert steps == 3                       # the exchange's step counter advanced once per forward

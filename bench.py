@@ -14,13 +14,19 @@ Workloads
                                B/N rows per GPU with all-gather + reduce-scatter ("strong")
   weak1024_d1024               1024 rows per GPU, global batch 1024*N (BASELINE configs[2])
   dense_b1024_d1024 / dense_b1024_d128   BASELINE configs[1] (launch-latency-bound)
-  stress_b65536_d512           BASELINE configs[3] (needs N >= 2 for the 180 GB budget at N=1 it fits too)
+  stress_b65536_d512           BASELINE configs[3] (global batch 65536, D = 512; sharded B/N rows per GPU)
+  index_b8192_d2048            the reference's OWN estimator (one rolled negative per row, loss.py:204-222; fp32,
+                               D = 2048 = the reference's projection width): HBM-bound fused kernel, roofline
+                               bound "hbm"; per-rank loss as in the reference (8192 rows per GPU, no exchange)
 
 Prints ONE JSON line on rank 0 (see the task contract): value = device-resident throughput,
 e2e = the same through host (pinned) buffers with H2D/D2H inside the timed region, roofline for
 the tcgen05 GEMM family, cpu_baseline = the oracle restatement timed on the host cores.
-`--impl reference` times the reference's CPU path (PyTorch fp32 restatement of loss.py's
-estimator in its dense form: the reference tree itself cannot travel to the GPU box).
+`--impl reference` times the reference's CPU path: the unmodified reference loss.py (Identity heads) when
+/root/reference is present and the workload has the reference's semantics (index_*), otherwise the PyTorch fp32
+restatement under oracle/ (the reference tree cannot travel to the GPU box; its loss has no dense mode).
+Every line carries "parity": loss / dF / dG / dt of the timed configuration against oracle.jsd_dense(_grads)
+(fp64, evaluated on the device, max over ranks) next to the BASELINE tolerances.
 """
 from __future__ import annotations
 
@@ -41,12 +47,24 @@ METRIC = "jsd_loss_fwd_bwd_pairs_per_s"
 UNIT = "pairs/s"
 WORKLOADS = {
     #  name                : (global batch at N=1, D, rows-per-gpu fixed?)
-    "dense_b8192_d1024": dict(batch=8192, dim=1024, weak=False),
-    "weak1024_d1024": dict(batch=1024, dim=1024, weak=True),
-    "dense_b1024_d1024": dict(batch=1024, dim=1024, weak=False),
-    "dense_b1024_d128": dict(batch=1024, dim=128, weak=False),
-    "stress_b65536_d512": dict(batch=65536, dim=512, weak=False),
+    "dense_b8192_d1024": dict(batch=8192, dim=1024, weak=False, mode="dense", dtype="bf16"),
+    "weak1024_d1024": dict(batch=1024, dim=1024, weak=True, mode="dense", dtype="bf16"),
+    "dense_b1024_d1024": dict(batch=1024, dim=1024, weak=False, mode="dense", dtype="bf16"),
+    "dense_b1024_d128": dict(batch=1024, dim=128, weak=False, mode="dense", dtype="bf16"),
+    "stress_b65536_d512": dict(batch=65536, dim=512, weak=False, mode="dense", dtype="bf16"),
+    "index_b8192_d2048": dict(batch=8192, dim=2048, weak=True, mode="index", dtype="f32"),
 }
+LOSS_RTOL, GRAD_RTOL = 1e-3, 1e-2   # BASELINE.json / BASELINE.md section 2
+
+
+def workload_config(args, wl):
+    """The `config` object of the JSON line: a function of (--workload, --gpus) only, so that both arms
+    (--impl b200 / reference) print the same one."""
+    batch = wl["batch"] * (args.gpus if wl["weak"] else 1)
+    return {"workload": args.workload, "global_batch": batch, "dim": wl["dim"],
+            "neg_mode": "dense (all off-diagonal pairs)" if wl["mode"] == "dense" else "shift1 (reference: text batch rolled by one)",
+            "input_dtype": wl["dtype"], "n_gpus": args.gpus,
+            "inputs": "N(0,1) features, text = 0.6 img + 0.8 noise, unit rows (SURVEY 8d), seed 0"}
 T_INIT = 2.659260036932778   # log(1/0.07), loss.py:82
 
 

@@ -199,17 +199,17 @@ bool fits_int(int64_t v) { return v > 0 && v < (int64_t)1 << 30; }
 template <typename T>
 int launch_index(const void* F, const void* G, int64_t B, int64_t D, const int32_t* neg, const int32_t* iptr,
                  const int32_t* iidx, const float* t_dev, float* coefp, float* partials, void* dF, void* dG,
-                 cudaStream_t st) {
+                 float grad_scale, cudaStream_t st) {
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) |
                                      reinterpret_cast<uintptr_t>(dF) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0;
   const unsigned grid = (unsigned)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA);
   const int threads = 32 * jsd::INDEX_ROWS_PER_CTA;
   if (vec)
     jsd::jsd_index_kernel<T, 4><<<grid, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr, iidx,
-                                                          t_dev, coefp, partials, (T*)dF, (T*)dG);
+                                                          t_dev, coefp, partials, (T*)dF, (T*)dG, grad_scale);
   else
     jsd::jsd_index_kernel<T, 1><<<grid, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr, iidx,
-                                                          t_dev, coefp, partials, (T*)dF, (T*)dG);
+                                                          t_dev, coefp, partials, (T*)dF, (T*)dG, grad_scale);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -296,7 +296,7 @@ int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; 
 
 extern "C" {
 
-int jsd_abi_version(void) { return 7; }
+int jsd_abi_version(void) { return 8; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -306,8 +306,10 @@ size_t jsd_index_workspace_bytes(int64_t B) { return (size_t)(B > 0 ? B : 0) * 4
 
 int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
                       const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
-                      float* out4, float* loss_out, void* dF, void* dG, jsd_stream_t stream) {
-  JSD_REQUIRE(F && G && t_dev && workspace && out4 && dF && dG, "jsd_index_fwd_bwd: null pointer argument");
+                      float* out4, float* loss_out, void* dF, void* dG, float grad_scale, jsd_stream_t stream) {
+  JSD_REQUIRE(F && G && t_dev && workspace && out4, "jsd_index_fwd_bwd: null pointer argument");
+  JSD_REQUIRE((dF == nullptr) == (dG == nullptr), "jsd_index_fwd_bwd: dF and dG must be given together");
+  JSD_REQUIRE(grad_scale > 0.f, "jsd_index_fwd_bwd: grad_scale must be positive");
   JSD_REQUIRE(fits_int(B) && fits_int(D), "jsd_index_fwd_bwd: B=%lld, D=%lld out of range", (long long)B, (long long)D);
   JSD_REQUIRE((neg_index == nullptr) == (inv_ptr == nullptr) && (inv_ptr == nullptr) == (inv_idx == nullptr),
               "jsd_index_fwd_bwd: neg_index, inv_ptr and inv_idx must be given together");
@@ -316,7 +318,7 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
   float* partials = coefp + B;
   int rc = [&]() -> int {
     JSD_DISPATCH_DTYPE(dtype, (launch_index<T>(F, G, B, D, neg_index, inv_ptr, inv_idx, t_dev, coefp, partials, dF,
-                                               dG, st)));
+                                               dG, grad_scale, st)));
   }();
   if (rc) return rc;
   jsd::finalize_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>(

@@ -318,7 +318,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer CTA's barriers and TMEM are set up as well
+  __syncthreads();                             // (also after the cluster barrier: compute-sanitizer's racecheck does not
+                                               //  model barrier.cluster as ordering the allocator's shared-memory write)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 

@@ -118,7 +118,8 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(32 * INDEX_ROWS_PER_CTA)
 jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D, const int* __restrict__ neg_index,
                  const int* __restrict__ inv_ptr, const int* __restrict__ inv_idx, const float* __restrict__ t_dev,
-                 float* __restrict__ coefp, float* __restrict__ partials, T* __restrict__ dF, T* __restrict__ dG) {
+                 float* __restrict__ coefp, float* __restrict__ partials, T* __restrict__ dF, T* __restrict__ dG,
+                 float grad_scale) {
   __shared__ float cta_part[INDEX_ROWS_PER_CTA][3];
   const int lane = threadIdx.x & 31;
   const int wrow = threadIdx.x >> 5;
@@ -212,9 +213,14 @@ jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D,
     __syncwarp();
   }
 
+  // The stored gradients are those of upstream gradient 1 times `grad_scale` (the caller divides it out again in
+  // fp32): with fp16 features sigma / (B ||f||) would land in the subnormals before GradScaler's factor is applied.
+  // dF == nullptr: forward only (eval / no_grad), the write-back pass is skipped.
+  if (dF != nullptr) {
   T* dfj = dF + (size_t)j * D;
   T* dgj = dG + (size_t)j * D;
   const float ca = tau * a, cb = tau * b;
+  const float inv_fs = inv_f * grad_scale, inv_gs = inv_g * grad_scale;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
       const float4 f = Vec4<T>::load(fj + d), g = Vec4<T>::load(gj + d), h = Vec4<T>::load(gn + d);
@@ -237,8 +243,8 @@ jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D,
 #define JSD_IDX_ELT(c)                                                            \
   {                                                                               \
     const float u = f.c * inv_f, v = g.c * inv_g, vn = h.c * inv_gn;              \
-    of.c = (ca * v + cb * vn - u * udot) * inv_f;                                 \
-    og.c = (ca * u + acc.c - v * vdot) * inv_g;                                   \
+    of.c = (ca * v + cb * vn - u * udot) * inv_fs;                                \
+    og.c = (ca * u + acc.c - v * vdot) * inv_gs;                                  \
   }
       JSD_IDX_ELT(x) JSD_IDX_ELT(y) JSD_IDX_ELT(z) JSD_IDX_ELT(w)
 #undef JSD_IDX_ELT
@@ -256,10 +262,11 @@ jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D,
         }
       }
       const float u = f * inv_f, v = g * inv_g, vn = h * inv_gn;
-      dfj[d] = from_f32<T>((ca * v + cb * vn - u * udot) * inv_f);
-      dgj[d] = from_f32<T>((ca * u + acc - v * vdot) * inv_g);
+      dfj[d] = from_f32<T>((ca * v + cb * vn - u * udot) * inv_fs);
+      dgj[d] = from_f32<T>((ca * u + acc - v * vdot) * inv_gs);
     }
   });
+  }  // dF != nullptr
   __syncwarp();
   if (lane == 0) {
     cta_part[wrow][0] = softplus_f(-s_pos);

@@ -76,10 +76,12 @@ def sm_count() -> int:
 
 # ------------------------------------------------------------------ index mode
 def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[torch.Tensor] = None,
-                  inv_ptr: Optional[torch.Tensor] = None, inv_idx: Optional[torch.Tensor] = None):
-    """Reference-semantics estimator, fused fwd+bwd.  Returns (out4, loss, dF, dG):
-    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), loss = 0-dim copy of out4[2], dF/dG for
-    upstream gradient 1."""
+                  inv_ptr: Optional[torch.Tensor] = None, inv_idx: Optional[torch.Tensor] = None,
+                  want_grad: bool = True, grad_scale: Optional[float] = None):
+    """Reference-semantics estimator, fused fwd+bwd.  Returns (out4, loss, dF, dG, grad_scale):
+    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), loss = 0-dim copy of out4[2], dF/dG = grad_scale times the
+    gradients for upstream gradient 1 (None with want_grad=False).  grad_scale defaults to B: the per-row
+    coefficients are sigma / B, which fp16 storage would flush to subnormals before a GradScaler factor applies."""
     _req(f, "F", ndim=2)
     _req(g, "G", dtype=f.dtype, ndim=2)
     if f.shape != g.shape:
@@ -93,16 +95,17 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
             if ix.numel() != n:
                 raise ValueError(f"{name} must have {n} entries")
     tt = _scalar(t, "temperature")
+    gs = float(b) if grad_scale is None else float(grad_scale)
     lib = _lib.load()
     ws = torch.empty(lib.jsd_index_workspace_bytes(b) // 4, dtype=torch.float32, device=f.device)
     out4 = torch.empty(4, dtype=torch.float32, device=f.device)
     loss = torch.empty((), dtype=torch.float32, device=f.device)
-    df = torch.empty_like(f)
-    dg = torch.empty_like(g)
+    df = torch.empty_like(f) if want_grad else None
+    dg = torch.empty_like(g) if want_grad else None
     with _on_device(f.device):
         _lib.call("jsd_index_fwd_bwd", _ptr(f), _ptr(g), _code(f), b, d, _ptr(neg_index), _ptr(inv_ptr),
-                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(loss), _ptr(df), _ptr(dg), _stream())
-    return out4, loss, df, dg
+                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(loss), _ptr(df), _ptr(dg), gs, _stream())
+    return out4, loss, df, dg, gs
 
 
 # ------------------------------------------------------------------ dense mode

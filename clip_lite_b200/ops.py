@@ -71,13 +71,17 @@ def _common(f: torch.Tensor, g: torch.Tensor):
 class _JSDIndexFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f, g, t, neg: Optional[NegativeIndex]):
+        need_grad = any(ctx.needs_input_grad)
         with torch.autocast("cuda", enabled=False):
             fc, gc = _common(f, g)
             if neg is not None and neg.n != fc.shape[0]:
                 raise ValueError(f"neg_index has {neg.n} entries for a batch of {fc.shape[0]}")
             ix = neg.on(fc.device) if neg is not None else (None, None, None)
-            out4, loss, df, dg = K.index_fwd_bwd(fc, gc, t, *ix)
-        ctx.save_for_backward(df, dg, out4)
+            # eval / no_grad: the kernel skips its write-back pass
+            out4, loss, df, dg, scale = K.index_fwd_bwd(fc, gc, t, *ix, want_grad=need_grad)
+        if need_grad:
+            ctx.save_for_backward(df, dg, out4)
+            ctx.inv_scale = 1.0 / scale
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         ctx.mark_non_differentiable(out4)
         return loss, out4
@@ -85,9 +89,13 @@ class _JSDIndexFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
         df, dg, out4 = ctx.saved_tensors
+        # the stored gradients carry the kernel's grad_scale; the product with the upstream gradient is formed in
+        # fp32 and rounded to the feature dtype ONCE (an fp16 product would round twice and underflow before a
+        # GradScaler factor could lift it)
         go = grad_loss.float()
+        gs = go * ctx.inv_scale
         fd, gd, td = ctx.dtypes
-        return (go * df).to(fd), (go * dg).to(gd), (go * out4[3]).to(td), None
+        return (gs * df.float()).to(fd), (gs * dg.float()).to(gd), (go * out4[3]).to(td), None
 
 
 class _JSDDenseFn(torch.autograd.Function):

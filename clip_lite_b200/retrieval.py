@@ -26,6 +26,9 @@ from . import _lib
 from . import kernels as K
 
 
+NO_TARGET_RANK = 2 ** 31 - 1     # rank reported for a row / column that has no ground truth (reference: 1e20)
+
+
 def prepare_operand(x: torch.Tensor, side: int, normalize: bool = False, precision: str = "bf16x3") -> torch.Tensor:
     """bf16 operand of the score kernel: [rows, 3 D] split form (side 0 = images/rows, 1 = texts/columns) or,
     with precision="bf16", the plain bf16 rounding [rows, D]."""
@@ -85,13 +88,19 @@ def retrieval_ranks(image_embeds: torch.Tensor, text_embeds: torch.Tensor,
         ct = torch.as_tensor(col_targets).to(device=dev, dtype=torch.int32).contiguous()
         if ct.numel() != n:
             raise ValueError(f"col_targets has {ct.numel()} entries for {n} texts")
-        if int(ct.max()) >= m:
-            raise ValueError("column target out of range")
+        if int(ct.max()) >= m or int(ct.min()) < -1:
+            raise ValueError("column target out of range (valid: image rows 0..M-1, or -1 for 'no ground-truth image')")
         thr_c = torch.empty(n, dtype=torch.float32, device=dev)
         rank_c = torch.empty(n, dtype=torch.int32, device=dev)
     with K._on_device(dev):
         _lib.call("jsd_score_ranks", a.data_ptr(), b.data_ptr(), m, n, k, K._ptr(ptr), K._ptr(idx), K._ptr(ct),
                   K._ptr(thr_r), K._ptr(thr_c), K._ptr(rank_r), K._ptr(rank_c), K._stream())
+    # a row / column without any ground truth never counts as retrieved: the reference leaves such an image at
+    # rank = 1e20 (retrieval.py:166), i.e. outside every recall@k
+    if rank_r is not None:
+        rank_r.masked_fill_(ptr[1:] == ptr[:-1], NO_TARGET_RANK)
+    if rank_c is not None:
+        rank_c.masked_fill_(ct < 0, NO_TARGET_RANK)
     return rank_r, rank_c
 
 

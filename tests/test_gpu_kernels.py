@@ -79,8 +79,12 @@ def test_index_vs_oracle(K, dtype, b, d, mode):
     if neg is not None:
         ptr, idx = _csr_inverse(neg, b)
         args = dict(neg_index=neg.int().cuda(), inv_ptr=ptr.cuda(), inv_idx=idx.cuda())
-    out4, loss, df, dg = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), **args)
+    out4, loss, df, dg, gs = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), **args)
+    df, dg = df.float() / gs, dg.float() / gs     # stored gradients carry grad_scale (= B by default)
     assert torch.equal(loss, out4[2])
+    # forward only (eval / no_grad): same loss, no gradient buffers
+    o4, l2, n1, n2, _ = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), want_grad=False, **args)
+    assert n1 is None and n2 is None and torch.equal(o4, out4)
     ref = orc.jsd_index(f.double(), g.double(), T0, neg)
     rdf, rdg, rdt = orc.jsd_index_grads(f.double(), g.double(), T0, neg)
     assert relerr(out4[0], ref["pos"]) < 1e-5
@@ -115,13 +119,33 @@ def test_index_vs_reference_golden(K, golden_dir):
         if neg is not None:
             ptr, idx = _csr_inverse(neg, f.shape[0])
             args = dict(neg_index=neg.int().cuda(), inv_ptr=ptr.cuda(), inv_idx=idx.cuda())
-        out4, _, df, dg = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(float(z["t"])), **args)
+        out4, _, df, dg, gs = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(float(z["t"])), **args)
+        df, dg = df / gs, dg / gs
         cross = float(z["out_cross_modal_loss"])
         assert abs(float(out4[2]) - cross) <= LOSS_RTOL * abs(cross), path
         # golden grads are d(total_loss) = 0.9 * d(cross)
         assert relerr(0.9 * df, torch.from_numpy(gf)) < 1e-4, path
         assert relerr(0.9 * dg, torch.from_numpy(gg)) < 1e-4, path
         assert relerr(0.9 * out4[3], torch.from_numpy(z["grad_temperature"])) < 1e-4, path
+
+
+def test_index_fp16_gradients_survive_loss_scaling():
+    """fp16 features with large norms: the unscaled per-element gradient sigma / (B ||f||) is below fp16's
+    normal range; the kernel stores it times B and ops applies the upstream gradient (GradScaler's factor) in
+    fp32 before the single rounding to fp16 (ops.py:90)."""
+    from clip_lite_b200 import ops
+    b, d = 4096, 256
+    f, g = orc.synth_embeddings(b, d, seed=3, correlated=True)
+    f, g = (f * 40).half(), (g * 40).half()
+    fl, gl = f.cuda().requires_grad_(True), g.cuda().requires_grad_(True)
+    t = dev_t().requires_grad_(True)
+    scale = 65536.0
+    loss, _ = ops.jsd_index_loss(fl, gl, t)
+    (loss * scale).backward()
+    rdf, rdg, _ = orc.jsd_index_grads(f.double(), g.double(), T0, None)
+    assert float(rdf.abs().max()) < 6.2e-5            # unscaled: fp16-subnormal territory
+    assert relerr(fl.grad.double() / scale, rdf) < GRAD_RTOL
+    assert relerr(gl.grad.double() / scale, rdg) < GRAD_RTOL
 
 
 # ------------------------------------------------------------------ tensor-core GEMM (tcgen05 + TMA)

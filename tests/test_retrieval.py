@@ -126,10 +126,22 @@ def test_one_sided_and_missing_targets():
     none_r, only_c = R.retrieval_ranks(img.cuda(), txt.cuda(), None, torch.tensor(cols))
     assert none_c is None and none_r is None
     assert torch.equal(only_r, both[0]) and torch.equal(only_c, both[1])      # deterministic integer counts
-    rows[7] = []                                                              # a row without ground truth ranks 0
+    # a row / column without ground truth is never "retrieved" (reference: rank = 1e20, retrieval.py:166)
+    rows[7] = []
     cols[3] = -1
     r, c = R.retrieval_ranks(img.cuda(), txt.cuda(), rows, torch.tensor(cols))
-    assert int(r[7]) == 0 and int(c[3]) == 0
+    assert int(r[7]) == R.NO_TARGET_RANK and int(c[3]) == R.NO_TARGET_RANK
+    keep_r = torch.ones(len(rows), dtype=torch.bool); keep_r[7] = False
+    keep_c = torch.ones(len(cols), dtype=torch.bool); keep_c[3] = False
+    assert torch.equal(r.cpu()[keep_r], both[0].cpu()[keep_r]) and torch.equal(c.cpu()[keep_c], both[1].cpu()[keep_c])
+    assert R.recall_metrics(r, c)["txt_r10"] <= R.recall_metrics(*both)["txt_r10"]
+    cols[3] = -2                                                              # invalid sentinel
+    with pytest.raises(ValueError):
+        R.retrieval_ranks(img.cuda(), txt.cuda(), rows, torch.tensor(cols))
+    cols[3] = len(rows)                                                       # beyond the last image row
+    with pytest.raises(ValueError):
+        R.retrieval_ranks(img.cuda(), txt.cuda(), rows, torch.tensor(cols))
+    cols[3] = -1
     with pytest.raises(ValueError):
         R.retrieval_ranks(img.cuda(), txt.cuda(), None, None)
     with pytest.raises(RuntimeError):

@@ -151,34 +151,73 @@ def cpu_dense_step(f, g, t, row_offset=0):
     tt = torch.tensor(t, dtype=torch.float32, requires_grad=True)
     out = orc.jsd_dense(fl, gl, tt, row_offset=row_offset)
     out["loss"].backward()
-    return float(out["loss"])
+    return float(out["loss"].detach())
 
 
-def time_cpu(batch, dim, budget_s, steps=None, warmup=1):
-    """Times the CPU restatement on a bounded sample: a row slab of `rows` image rows against all
-    `batch` text rows (work per row is constant, so pairs/s = rows / t is the whole-problem rate)."""
+def _cpu_index_stepper():
+    """(step(f, g), kind): one fwd + backward() of the reference's own estimator on (B, D) embeddings.  With the
+    reference tree present (build container) this is the UNMODIFIED reference loss.py with Identity projection
+    heads (kind "reference"); on the GPU box, where /root/reference does not exist, the oracle's
+    restatement of the same lines (loss.py:94-105,204-222,254; kind "port")."""
+    from oracle import jsd_oracle as orc
+    from oracle import reference_loader as rl
+    if rl.reference_available():
+        mod = rl.reference_estimator_module()
+
+        def step(f, g):
+            fl = f.detach().clone().requires_grad_(True)
+            gl = g.detach().clone().requires_grad_(True)
+            mod.zero_grad(set_to_none=True)
+            with rl.cuda_calls_neutralised():
+                out = mod(image_features=fl, text_features=gl)
+            out["cross_modal_loss"].backward()
+            return float(out["cross_modal_loss"].detach())
+        return step, "reference"
+
+    def step(f, g):
+        fl = f.detach().clone().requires_grad_(True)
+        gl = g.detach().clone().requires_grad_(True)
+        tt = torch.tensor(T_INIT, dtype=torch.float32, requires_grad=True)
+        out = orc.jsd_index(fl, gl, tt)
+        out["loss"].backward()
+        return float(out["loss"].detach())
+    return step, "port"
+
+
+def time_cpu(wl, batch, dim, budget_s, steps=None, warmup=1):
+    """Times the CPU path on a bounded sample of the workload.  Dense: a row slab of `rows` image rows against
+    all `batch` text rows (work per row is constant, so pairs/s = rows / t is the whole-problem rate).  Index
+    (reference semantics): the first `rows` pairs (work per pair is constant)."""
     torch.set_num_threads(os.cpu_count() or 1)
     f, g = synth(batch, dim)
     f, g = f.float(), g.float()
-    rows = min(batch, 256)
-    cpu_dense_step(f[:rows], g, T_INIT)                      # first call pays one-off thread-pool start-up
+    if wl["mode"] == "index":
+        stepper, kind = _cpu_index_stepper()
+        run = lambda r: stepper(f[:r], g[:r])
+        rows, what = batch, "index-mode (one rolled negative per row) fwd+backward() of {rows} pairs"
+    else:
+        kind = "port"
+        run = lambda r: cpu_dense_step(f[:r], g, T_INIT)
+        rows, what = min(batch, 256), "dense fwd+backward() of a {rows}x{batch} row slab"
+    run(rows)                                                # first call pays one-off thread-pool start-up
     t0 = time.perf_counter()
-    cpu_dense_step(f[:rows], g, T_INIT)
+    run(rows)
     probe = max(time.perf_counter() - t0, 1e-4)
     n_steps = steps if steps is not None else 3
     per_step = budget_s / (n_steps + warmup)
     rows = int(min(batch, max(64, rows * per_step / probe)))
     rows = max(64, rows // 64 * 64)
     for _ in range(warmup):
-        cpu_dense_step(f[:rows], g, T_INIT)
+        run(rows)
     times = []
     for _ in range(n_steps):
         t0 = time.perf_counter()
-        cpu_dense_step(f[:rows], g, T_INIT)
+        run(rows)
         times.append(time.perf_counter() - t0)
     mean = sum(times) / len(times)
-    return {"value": rows / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"dense fwd+backward() of a {rows}x{batch} row slab, D={dim}, fp32 torch CPU, "
+    src = {"reference": "the unmodified reference loss.py (Identity heads)", "port": "oracle/ restatement"}[kind]
+    return {"value": rows / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": what.format(rows=rows, batch=batch) + f", D={dim}, fp32 torch CPU ({src}), "
                       f"{n_steps} steps after {warmup} warm-up (mean {mean*1e3:.1f} ms/step)"}, mean, rows
 
 
@@ -186,19 +225,65 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch, dim = wl["batch"] * (args.gpus if wl["weak"] else 1), wl["dim"]
-    base, mean, rows = time_cpu(batch, dim, budget_s=150.0, steps=args.steps, warmup=max(args.warmup, 1))
+    cfg = workload_config(args, wl)
+    batch, dim = cfg["global_batch"], wl["dim"]
+    base, mean, rows = time_cpu(wl, batch, dim, budget_s=150.0, steps=args.steps, warmup=max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
         "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "neg_mode": "dense",
-                   "sample_rows": rows, "device": "host CPU"},
+        "config": cfg,
+        "details": {"device": "host CPU", "sample_rows": rows},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ parity of the timed configuration
+def _rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def parity_dense(step_out, f_all, g_all, rank, rows, dev, world, dist):
+    """Loss / dF / dG / dt of this rank's step against oracle.jsd_dense(_grads) in fp64 ON THE DEVICE (checker
+    only), inputs = the very bf16 features the step consumed, up-cast.  dF and the loss need this rank's ROW slab
+    of the score matrix, dG its COLUMN slab (= the row slab of the transposed problem), so the check scales to
+    BASELINE configs[3] (8192 x 65536 fp64 per slab).  Errors are the max over ranks."""
+    from oracle import jsd_oracle as orc
+    loss, df, dg, dt = step_out
+    lo, hi = rank * rows, (rank + 1) * rows
+    f64, g64 = f_all.to(dev).double(), g_all.to(dev).double()
+    ref = orc.jsd_dense(f64[lo:hi], g64, T_INIT, row_offset=lo)
+    rdf, _, rdt = orc.jsd_dense_grads(f64[lo:hi], g64, T_INIT, row_offset=lo)
+    rdg, _, _ = orc.jsd_dense_grads(g64[lo:hi], f64, T_INIT, row_offset=lo)     # transposed problem: column slab
+    errs = torch.tensor([_rel(loss, ref["loss"]), _rel(df, rdf), _rel(dg, rdg), _rel(dt, rdt)],
+                        device=dev, dtype=torch.float64)
+    del f64, g64, rdf, rdg
+    if world > 1:
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    e = [float(x) for x in errs]
+    return {"loss_rel": e[0], "dF_rel": e[1], "dG_rel": e[2], "dt_rel": e[3],
+            "tol": {"loss": LOSS_RTOL, "grad": GRAD_RTOL},
+            "ok": bool(e[0] <= LOSS_RTOL and max(e[1:]) <= GRAD_RTOL),
+            "against": "oracle.jsd_dense / jsd_dense_grads, fp64 on the device, same bf16 inputs up-cast; "
+                       "max-norm relative error per tensor, max over ranks"}
+
+
+def parity_index(step_out, f, g):
+    from oracle import jsd_oracle as orc
+    loss, df, dg, dt = step_out
+    f64, g64 = f.detach().double(), g.detach().double()
+    ref = orc.jsd_index(f64, g64, T_INIT)
+    rdf, rdg, rdt = orc.jsd_index_grads(f64, g64, T_INIT)
+    e = [_rel(loss, ref["loss"]), _rel(df, rdf), _rel(dg, rdg), _rel(dt, rdt)]
+    return {"loss_rel": e[0], "dF_rel": e[1], "dG_rel": e[2], "dt_rel": e[3],
+            "tol": {"loss": LOSS_RTOL, "grad": GRAD_RTOL},
+            "ok": bool(e[0] <= LOSS_RTOL and max(e[1:]) <= GRAD_RTOL),
+            "against": "oracle.jsd_index / jsd_index_grads (= reference loss.py:204-222, golden-pinned), fp64 on "
+                       "the device, same inputs; max-norm relative error per tensor"}
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -217,12 +302,15 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    batch = wl["batch"] * (world if wl["weak"] else 1)
-    dim = wl["dim"]
+    cfg = workload_config(args, wl)
+    batch, dim = cfg["global_batch"], wl["dim"]
+    index_mode = wl["mode"] == "index"
     if batch % world:
         raise SystemExit("global batch must divide by the number of GPUs")
     rows = batch // world
     f_all, g_all = synth(batch, dim)
+    if wl["dtype"] == "f32":
+        f_all, g_all = f_all.float(), g_all.float()
     f_host = f_all[rank * rows:(rank + 1) * rows].contiguous().pin_memory()
     g_host = g_all[rank * rows:(rank + 1) * rows].contiguous().pin_memory()
     f_dev = f_host.to(dev).requires_grad_(True)
@@ -230,15 +318,16 @@ def run_b200(args, wl):
     t_dev = torch.tensor(T_INIT, device=dev, requires_grad=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    # N > 1: the two exchange steps either fused into the kernels over NVLink peer memory (default) or as NCCL
-    # collectives (--exchange nccl); a peer set-up failure (no CUDA IPC on the box) is reported and NCCL used
-    exchange = "none"
-    if world > 1:
+    # N > 1, dense: the two exchange steps either fused into the kernels over NVLink peer memory (default) or as NCCL
+    # collectives (--exchange nccl); a peer set-up failure (no CUDA IPC on the box) is reported and NCCL used.
+    # Index mode has the reference's per-rank loss: every rank works on its own rows, nothing is exchanged.
+    exchange, partials = "none", None
+    if world > 1 and not index_mode:
         exchange = args.exchange
         if exchange == "peer":
             try:
                 from clip_lite_b200 import peer
-                peer.get_exchange(rows, dim)
+                partials = peer.get_exchange(rows, dim).partials
             except Exception as exc:
                 print(f"[bench] peer exchange unavailable ({type(exc).__name__}: {exc}); NCCL collectives",
                       file=sys.stderr)
@@ -248,6 +337,8 @@ def run_b200(args, wl):
             exchange = "peer" if int(ok) == 1 else "nccl"
 
     def loss_fn(f, g):
+        if index_mode:
+            return ops.jsd_index_loss(f, g, t_dev)[0]
         if exchange == "peer":
             return peer.peer_dense_loss(f, g, t_dev, route=args.route)[0]
         if world > 1:
@@ -263,7 +354,7 @@ def run_b200(args, wl):
     step, graphed = eager_step, False
     if args.cuda_graph:
         try:
-            if world == 1:
+            if world == 1 or index_mode:
                 from clip_lite_b200.graph import GraphedStep
                 gs = GraphedStep(lambda f, g, t: loss_fn(f, g), f_dev, g_dev, t_dev)
             elif exchange == "peer":   # no collective call in the step: one graph launch per step
@@ -301,7 +392,30 @@ def run_b200(args, wl):
 
     for _ in range(max(args.warmup, 3)):
         out = step()
-    loss_value = float(out[0])
+    torch.cuda.synchronize()
+    loss_value = float(out[0].detach())
+
+    # ---- parity of exactly what is timed (the step's own outputs) against the oracle, before the clock starts
+    parity = None
+    if not args.no_parity:
+        try:
+            if index_mode:
+                parity = parity_index(out, f_dev, g_dev)
+                if world > 1:
+                    worst = torch.tensor([parity[k] for k in ("loss_rel", "dF_rel", "dG_rel", "dt_rel")], device=dev,
+                                         dtype=torch.float64)
+                    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+                    for k, v in zip(("loss_rel", "dF_rel", "dG_rel", "dt_rel"), worst.tolist()):
+                        parity[k] = v
+                    parity["ok"] = bool(parity["loss_rel"] <= LOSS_RTOL and
+                                        max(parity["dF_rel"], parity["dG_rel"], parity["dt_rel"]) <= GRAD_RTOL)
+            else:
+                parity = parity_dense(out, f_all, g_all, rank, rows, dev, world, dist)
+        except Exception as exc:
+            parity = {"ok": None, "error": f"{type(exc).__name__}: {exc}"}
+            if world > 1:
+                raise
+        torch.cuda.empty_cache()
 
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step, args.steps)
@@ -337,7 +451,7 @@ def run_b200(args, wl):
             if i + 1 < steps:
                 issue_h2d(slot ^ 1)
             main.wait_event(h2d_done[slot])
-            if graphed and world > 1:
+            if graphed and world > 1 and not index_mode:
                 # sharded step: eager launches (~0.44 ms of host work) would exceed the 0.3 ms H2D copy
                 loss = step(stage[slot][0], stage[slot][1])[0]
             else:
@@ -361,104 +475,121 @@ def run_b200(args, wl):
     e2e_run(3)
     e2e_steps = max(5, min(args.steps, 100))
     e2e_ms = e2e_run(e2e_steps) / e2e_steps
+    esize = f_host.element_size()
     e2e = {"value": batch / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": 2 * rows * dim * 2, "d2h_bytes_per_step": 4,
-           "note": "inputs from pinned host memory every step (H2D of step i+1 overlaps step i on a copy stream); "
-                   "the loss is read back to the host every step, gradients stay on the device as in training"}
+           "h2d_bytes_per_step": 2 * rows * dim * esize, "d2h_bytes_per_step": 4, "input_dtype": wl["dtype"],
+           "note": f"inputs ({wl['dtype']} features, the dtype named in config.input_dtype) from pinned host memory "
+                   "every step (H2D of step i+1 overlaps step i on a copy stream); the loss is read back to the host "
+                   "every step, gradients stay on the device as in training"}
 
-    # ---- roofline of the dominant kernel family (the three tcgen05 GEMM launches of a step),
-    # timed live with CUDA events around each launch on the launching stream
     peak_tf, peak_gbs, peak_src = load_peaks()
-    with torch.no_grad():
-        u, inv_f = K.normalize_cast(f_dev.detach())
-        v, inv_g = K.normalize_cast(g_dev.detach())
-        if world > 1:
-            v_all = torch.empty(batch, dim, dtype=torch.bfloat16, device=dev)
-            dist.all_gather_into_tensor(v_all, v)
-        else:
-            v_all = v
-        gamma = torch.ones((), device=dev)
-        t_c = t_dev.detach()
-        _, _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
-        stages = {
-            "fwd": lambda: K.dense_fwd(u, v_all, t_c, row_offset=rank * rows),
-            "bwd_du": lambda: K.dense_bwd_du(gmat, v_all, t_c, gamma),
-            "bwd_dv": lambda: K.dense_bwd_dv(gmat, u, batch, t_c, gamma),
-        }
-        stage_ms = {}
-        n_meas = max(5, min(args.steps, 50))
-        for name, fn in stages.items():
-            for _ in range(3):
-                fn()
-            stage_ms[name] = timed(fn, n_meas) / n_meas
-    # ---- N > 1: the same row slab with pre-gathered operands and NO exchange (the numerator of
-    # the weak-scaling efficiency E(R) = t_slab_nocomm / t_step); replayed from a CUDA graph like the step itself
+    n_meas = max(5, min(args.steps, 50))
     slab_nocomm_ms = None
-    if world > 1:
-        f_c, g_c = f_dev.detach(), g_dev.detach()
-
-        def local_slab():
-            uu, vv, i_f, i_g = K.normalize_cast_pair(f_c, g_c)
-            _, _, gm, gd = K.dense_fwd(uu, v_all, t_c, row_offset=rank * rows)
-            dv_part = K.dense_bwd_dv(gm, uu, batch, t_c, gamma)
-            K.dense_backward_image_side(f_c, v_all, i_f, gm, gd, t_c, gamma, rank * rows)
-            K.normalize_bwd(g_c, i_g, dv_part[rank * rows:(rank + 1) * rows], uu, 0, gd, t_c, gamma, rows)
-
-        try:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side), torch.no_grad():
-                local_slab()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr), torch.no_grad():
-                local_slab()
+    if index_mode:
+        # ---- roofline of the fused index kernel (HBM-bound): read F, G once, write dF, dG once
+        with torch.no_grad():
+            fd, gd, tc = f_dev.detach(), g_dev.detach(), t_dev.detach()
             for _ in range(3):
-                gr.replay()
-            slab_nocomm_ms = timed(gr.replay, n_meas) / n_meas
-        except Exception as exc:
-            print(f"[bench] slab-without-exchange timing failed ({type(exc).__name__}: {exc})", file=sys.stderr)
-            torch.cuda.synchronize()
-    flops_per_launch = 2.0 * rows * batch * dim                       # S = U V^T, dU = G V, dV = G^T U
-    gemm_ms = sum(stage_ms.values())
-    achieved = 3 * flops_per_launch / (gemm_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload if world == 1 else "", None)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "jsd_gemm_kernel (tcgen05, 3 launches/step: fwd, dU, dV)",
-                "algorithmic_flops_per_launch": flops_per_launch,
-                "launch_ms": stage_ms,
-                "step_frac_of_peak": 3 * flops_per_launch / (ms_per_step * 1e-3) / 1e12 / peak_tf}
+                K.index_fwd_bwd(fd, gd, tc)
+            k_ms = timed(lambda: K.index_fwd_bwd(fd, gd, tc), n_meas) / n_meas
+        alg_bytes = 4.0 * rows * dim * esize
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                    "traffic": _traffic(args.workload), "peak_source": peak_src,
+                    "kernel": "jsd_index_kernel (+ 1-block finalize), one call per step",
+                    "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": {"index_fwd_bwd": k_ms},
+                    "step_frac_of_peak": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs}
+        launches_per_step = 2
+        tflops = None
+    else:
+        # ---- roofline of the dominant kernel family (the three tcgen05 GEMM launches of a step),
+        # timed live with CUDA events around each launch on the launching stream
+        with torch.no_grad():
+            u, inv_f = K.normalize_cast(f_dev.detach())
+            v, inv_g = K.normalize_cast(g_dev.detach())
+            if world > 1:
+                v_all = torch.empty(batch, dim, dtype=torch.bfloat16, device=dev)
+                dist.all_gather_into_tensor(v_all, v)
+            else:
+                v_all = v
+            gamma = torch.ones((), device=dev)
+            t_c = t_dev.detach()
+            _, _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
+            stages = {
+                "fwd": lambda: K.dense_fwd(u, v_all, t_c, row_offset=rank * rows),
+                "bwd_du": lambda: K.dense_bwd_du(gmat, v_all, t_c, gamma),
+                "bwd_dv": lambda: K.dense_bwd_dv(gmat, u, batch, t_c, gamma),
+            }
+            stage_ms = {}
+            for name, fn in stages.items():
+                for _ in range(3):
+                    fn()
+                stage_ms[name] = timed(fn, n_meas) / n_meas
+        # ---- N > 1: the same row slab with pre-gathered operands and NO exchange (the numerator of
+        # the weak-scaling efficiency E(R) = t_slab_nocomm / t_step); replayed from a CUDA graph like the step itself
+        if world > 1:
+            f_c, g_c = f_dev.detach(), g_dev.detach()
+
+            def local_slab():
+                uu, vv, i_f, i_g = K.normalize_cast_pair(f_c, g_c)
+                _, _, gm, gd = K.dense_fwd(uu, v_all, t_c, row_offset=rank * rows)
+                dv_part = K.dense_bwd_dv(gm, uu, batch, t_c, gamma)
+                K.dense_backward_image_side(f_c, v_all, i_f, gm, gd, t_c, gamma, rank * rows)
+                K.normalize_bwd(g_c, i_g, dv_part[rank * rows:(rank + 1) * rows], uu, 0, gd, t_c, gamma, rows)
+
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side), torch.no_grad():
+                    local_slab()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr), torch.no_grad():
+                    local_slab()
+                for _ in range(3):
+                    gr.replay()
+                slab_nocomm_ms = timed(gr.replay, n_meas) / n_meas
+            except Exception as exc:
+                print(f"[bench] slab-without-exchange timing failed ({type(exc).__name__}: {exc})", file=sys.stderr)
+                torch.cuda.synchronize()
+        flops_per_launch = 2.0 * rows * batch * dim                       # S = U V^T, dU = G V, dV = G^T U
+        gemm_ms = sum(stage_ms.values())
+        achieved = 3 * flops_per_launch / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "traffic": _traffic(args.workload) if world == 1 else None, "peak_source": peak_src,
+                    "kernel": "jsd_gemm_kernel (tcgen05, 3 launches/step: fwd, dU, dV)",
+                    "algorithmic_flops_per_launch": flops_per_launch,
+                    "launch_ms": stage_ms,
+                    "step_frac_of_peak": 3 * flops_per_launch / (ms_per_step * 1e-3) / 1e12 / peak_tf}
+        # library launches per step: normalise pair (+push), forward (+ loss), dU, dV, image Jacobian (helper
+        # stream), text Jacobian (+ dL/dt); with JSD_OVERLAP=0 one GPU runs both Jacobians in one launch;
+        # the symmetric route runs 2 pushes, 2 forwards, 2 contractions, 2 Jacobians
+        launches_per_step = 5 if (world == 1 and os.environ.get("JSD_OVERLAP", "1") == "0") else 6
+        if world > 1 and args.route == "symmetric":
+            launches_per_step = 8
+        tflops = 6.0 * rows * batch * dim / (ms_per_step * 1e-3) / 1e12
 
     line = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu, _, _ = time_cpu(batch, dim, budget_s=20.0)
-        # library launches per step: normalise pair (+push), forward (+ loss), dU, dV, image Jacobian (helper
-        # stream), text Jacobian (+ dL/dt); with JSD_OVERLAP=0 one GPU runs both Jacobians in one launch
-        launches_per_step = 5 if (world == 1 and os.environ.get("JSD_OVERLAP", "1") == "0") else 6
+            cpu, _, _ = time_cpu(wl, batch, dim, budget_s=20.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "global_batch": batch, "dim": dim, "rows_per_gpu": rows,
-                       "neg_mode": "dense", "parallelism": f"dp{world}", "cuda_graph": graphed, "exchange": exchange,
-                       "route": args.route if world > 1 else "none",
-                       "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
-                       "inputs": "bf16 unit rows resident in HBM; N(0,1) features, text = 0.6 img + 0.8 noise"},
+            "scaling": "weak" if wl["weak"] else "strong", "vs_baseline": None, "dtype": wl["dtype"],
+            "data": "synthetic", "config": cfg,
+            "details": {"rows_per_gpu": rows, "parallelism": f"dp{world}", "cuda_graph": graphed,
+                        "exchange": exchange, "route": args.route if exchange != "none" else "none",
+                        "grad_partials": partials,
+                        "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
+                        "inputs_resident": f"{wl['dtype']} unit rows resident in HBM before the timed region"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
-            "tflops_6B2D": 6.0 * rows * batch * dim / (ms_per_step * 1e-3) / 1e12,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "loss": loss_value,
         }
+        if tflops is not None:
+            line["tflops_6B2D"] = tflops
         if slab_nocomm_ms is not None:
             line["slab_nocomm"] = {"ms_per_step": slab_nocomm_ms,
                                    "note": "this rank's row slab with pre-gathered text rows and no exchange, same "
@@ -470,6 +601,16 @@ def run_b200(args, wl):
         print(json.dumps(line), flush=True)
 
 
+def _traffic(workload):
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            return json.load(open(tpath)).get(workload, None)
+        except Exception:
+            return None
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -478,6 +619,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="dense_b8192_d1024")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed step's outputs")
     ap.add_argument("--cuda-graph", type=int, default=1, help="replay the step as one CUDA graph (default 1)")
     ap.add_argument("--route", choices=["reduce", "symmetric"], default="reduce",
                     help="N > 1: text-side gradient by reducing the ranks' partials (measured default) or by also "

@@ -57,13 +57,15 @@ SIGNATURES = {
                                         c_void_p]),
     "jsd_peer_dense_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
-    "jsd_peer_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "jsd_peer_dense_bwd_dv": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                       c_void_p]),
     "jsd_peer_normalize_bwd_text": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                            c_void_p, c_void_p, c_void_p]),
+                                            c_void_p, c_int, c_void_p, c_void_p]),
     "jsd_peer_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_peer_set_timeout": (c_int, [ctypes.c_double]),
+    "jsd_peer_wait_error": (c_int, [c_void_p, c_void_p, c_void_p]),
     "jsd_split_bf16x3": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "jsd_score_ranks": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -112,9 +114,14 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+ERROR_HOOKS = []     # callables run (best effort) before a failing call raises, e.g. kernels._rearm_workspaces
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().jsd_last_error().decode("utf-8", "replace")
+        for hook in ERROR_HOOKS:
+            hook()
         raise JSDLibraryError(f"{what} failed: {msg}")
 
 

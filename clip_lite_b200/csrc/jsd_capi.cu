@@ -142,6 +142,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
   const int n_blocks = (p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N;
   const long long tiles = (long long)((p.M + jsd::BLOCK_M * CG - 1) / (jsd::BLOCK_M * CG)) * n_blocks;
   const long long work_items = tiles * (MODE == jsd::MODE_GRAD && p.ksplit > 1 ? p.ksplit : 1);   // split-K slices
+  if (MODE != jsd::MODE_GRAD) p.ksplit = 1;
   int workers = (int)(work_items < max_workers ? work_items : max_workers);
   // stream-K (opt-in: the caller passes a workspace), see SkPolicy
   p.stream_k = 0;
@@ -281,6 +282,48 @@ SideStream* side_stream() {
   return &s;
 }
 
+// Peer waits (ptx.cuh: WaitCfg): time limit + host-mapped error word, installed once per device.
+double g_wait_timeout_s = -1.0;
+unsigned long long g_wait_cfg_mask = 0;
+volatile int* g_wait_err_host = nullptr;
+
+int ensure_wait_cfg() {
+  int dev = 0;
+  JSD_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && ((g_wait_cfg_mask >> dev) & 1ull)) return 0;
+  if (g_wait_timeout_s <= 0.0) {
+    const char* e = getenv("JSD_PEER_TIMEOUT_S");
+    const double v = e ? atof(e) : 0.0;
+    g_wait_timeout_s = v > 0.0 ? v : 300.0;
+  }
+  if (g_wait_err_host == nullptr) {
+    int* h = nullptr;
+    if (cudaHostAlloc((void**)&h, 4 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      memset(h, 0, 4 * sizeof(int));
+      g_wait_err_host = h;
+    } else {
+      (void)cudaGetLastError();       // no mapped memory: the trap still fires, only the report is lost
+    }
+  }
+  jsd::WaitCfg cfg;
+  cfg.timeout_ns = (unsigned long long)(g_wait_timeout_s * 1e9);
+  cfg.err_host = const_cast<int*>(g_wait_err_host);
+  // (synchronous, not legal during a stream capture: the eager warm-up step every capture needs installs it)
+  JSD_CUDA_OK(cudaMemcpyToSymbol(jsd::g_wait_cfg, &cfg, sizeof(cfg)));
+  if (dev >= 0 && dev < 64) g_wait_cfg_mask |= 1ull << dev;
+  return 0;
+}
+
+// development knob: JSD_PEER_WAIT_ALL=1 makes the peer forward wait for every rank before its first load (round 1)
+bool peer_wait_per_source() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JSD_PEER_WAIT_ALL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // the second int of the forward workspace's 16-byte ticket area serialises the dL/dt reduction
 int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; }
 
@@ -368,6 +411,7 @@ struct PeerWait {
   const int* flags = nullptr;
   const int* counter = nullptr;
   int count = 0;
+  int rows = 0;        // rows per source rank (0: wait for every rank before the first load)
 };
 int dense_fwd_impl(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                    const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
@@ -423,6 +467,12 @@ int dense_fwd_impl(const void* U, const void* V, int64_t M, int64_t N, int64_t D
   p.wait_flags = wait.flags;
   p.wait_counter = wait.counter;
   p.wait_count = wait.count;
+  p.wait_rows = wait.rows;
+  if (wait.flags != nullptr && wait.rows > 0) {
+    // start on this rank's own column block, then walk the ranks in the order their rows arrive (rank - 1, ...
+    // see normalize_push_kernel): n-blocks are visited downwards from the own block
+    p.n_rot = (int)(row_offset / jsd::BLOCK_N);
+  }
   if (Gmat) {
     // epilogue TMA stores: box = 64 columns x 32 rows per warp; rows >= M / columns >= N are clipped
     if (int rc = make_tmap(&p.tmG, Gmat, N, M, ldg, jsd::COLS_PER_WARP, 32)) return rc;
@@ -725,6 +775,7 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
                             float* inv_f, float* inv_g, jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_normalize_push")) return rc;
   JSD_REQUIRE(F && G && U && inv_f && inv_g && (parity == 0 || parity == 1), "jsd_peer_normalize_push: bad argument");
+  if (int rc = ensure_wait_cfg()) return rc;
   const int64_t rows = ctx->rows, D = ctx->dim;
   jsd::PeerPushJob job{};
   job.X[0] = F;
@@ -733,22 +784,25 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
   job.inv_norm[0] = inv_f;
   job.inv_norm[1] = inv_g;
   uintptr_t bits = reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(U);
-  for (int q = 0; q < ctx->world; ++q) {
-    job.v_dst[q] = (__nv_bfloat16*)ctx->v_all[parity][q] + (size_t)ctx->rank * rows * D;
-    job.flag_dst[q] = ctx->flags[q] + JSD_PEER_READY_V + parity * JSD_MAX_PEERS + ctx->rank;
-    bits |= reinterpret_cast<uintptr_t>(job.v_dst[q]);
+  for (int k = 0; k < ctx->world; ++k) {
+    // destination slot k = rank - k (mod world): a receiver q is therefore served by q, q + 1, q + 2, ... in turn,
+    // the order in which its forward walks the column blocks
+    const int q = (ctx->rank - k + ctx->world) % ctx->world;
+    job.v_dst[k] = (__nv_bfloat16*)ctx->v_all[parity][q] + (size_t)ctx->rank * rows * D;
+    job.flag_dst[k] = ctx->flags[q] + JSD_PEER_READY_V + parity * JSD_MAX_PEERS + ctx->rank;
+    bits |= reinterpret_cast<uintptr_t>(job.v_dst[k]);
   }
   int32_t* mine = ctx->flags[ctx->rank];
   job.counter = mine + JSD_PEER_COUNTER_V + parity;
   job.ticket = mine + JSD_PEER_TICKET_PUSH;
   job.world = ctx->world;
-  const bool vec = (D % 4 == 0) && (bits & 15) == 0;
+  const bool vec = (D % 8 == 0) && (bits & 15) == 0;
   const dim3 grid((unsigned)((rows + 7) / 8), 2);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
 #define JSD_PUSH_CASE(code, T)                                                                        \
     case code:                                                                                        \
-      if (vec) jsd::normalize_push_kernel<T, 4><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);        \
+      if (vec) jsd::normalize_push_kernel<T, 8><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);        \
       else jsd::normalize_push_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);            \
       break;
     JSD_PUSH_CASE(JSD_F32, float)
@@ -766,28 +820,73 @@ int jsd_peer_dense_fwd(const void* U, const jsd_peer_ctx* ctx, int parity, const
                        jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_fwd")) return rc;
   JSD_REQUIRE(parity == 0 || parity == 1, "jsd_peer_dense_fwd: parity must be 0 or 1");
+  if (int rc = ensure_wait_cfg()) return rc;
   const int32_t* mine = ctx->flags[ctx->rank];
   PeerWait w;
   w.flags = mine + JSD_PEER_READY_V + parity * JSD_MAX_PEERS;
   w.counter = mine + JSD_PEER_COUNTER_V + parity;
   w.count = ctx->world;
+  w.rows = peer_wait_per_source() ? (int)ctx->rows : 0;
   return dense_fwd_impl(U, ctx->v_all[parity][ctx->rank], ctx->rows, ctx->rows * ctx->world, ctx->dim,
                         ctx->rows * ctx->rank, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, w, stream);
 }
 
+// dV partial as bf16 tiles pushed by TMA stores from the contraction's epilogue into the OWNER's slots
+// (stage[q] viewed as [world][rows][D] bf16: slot = source rank), owner blocks walked from rank + 1 on
+static int peer_dv_push(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
+                        const float* gamma_dev, jsd_stream_t stream) {
+  const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim;
+  JSD_REQUIRE(Gmat && U && t_dev, "jsd_peer_dense_bwd_dv: null pointer argument");
+  JSD_REQUIRE(D % 8 == 0 && ldg >= N && ldg % 8 == 0, "jsd_peer_dense_bwd_dv: bad D / ldg");
+  JSD_REQUIRE(M % 32 == 0, "jsd_peer_dense_bwd_dv: bf16 partials need rows per rank %% 32 == 0 (got %lld)", (long long)M);
+  const int cg = pick_cta_group(N);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap(&tmA, Gmat, N, M, ldg, 64, jsd::BLOCK_K)) return rc;       // Gmat^T read MN-major
+  if (int rc = make_tmap(&tmB, U, D, M, D, 64, jsd::BLOCK_K)) return rc;            // U [M, D] read MN-major
+  jsd::GemmParams p{};
+  p.M = (int)N;                     // rows of the output: every text row
+  p.N = (int)D;
+  p.K = (int)M;
+  p.n_fastest = tile_order(true, 1);
+  p.t_dev = t_dev;
+  p.gamma_dev = gamma_dev;
+  p.scale = N > 1 ? (float)(1.0 / ((double)M * (double)(N - 1))) : 0.f;
+  p.ksplit = 1;
+  p.peer_world = ctx->world;
+  int32_t* mine = ctx->flags[ctx->rank];
+  for (int q = 0; q < ctx->world; ++q) {
+    p.peer_flag_dst[q] = ctx->flags[q] + JSD_PEER_READY_DV + ctx->rank;
+    void* slot = (__nv_bfloat16*)ctx->stage[q] + (size_t)ctx->rank * M * D;         // this rank's slot at owner q
+    if (int rc = make_tmap(&p.tmPush[q], slot, D, M, D, jsd::COLS_PER_WARP, 32)) return rc;
+  }
+  p.peer_counter = mine + JSD_PEER_COUNTER_DV;
+  p.peer_ticket = mine + JSD_PEER_TICKET_DV;
+  p.push_ticket = mine + JSD_PEER_TICKET_DVPUSH;
+  p.push_rows = (int)M;
+  p.push_expected = (int)((M / 32) * ((D + jsd::COLS_PER_WARP - 1) / jsd::COLS_PER_WARP));
+  // first m-block of rank + 1's rows (own rows last: they need no link)
+  const int tile_m = jsd::BLOCK_M * cg;
+  p.m_rot = (int)((((int64_t)(ctx->rank + 1) % ctx->world) * M) / tile_m);
+  cudaStream_t st = (cudaStream_t)stream;
+  return cg == 2 ? launch_gemm<jsd::MODE_GRADPUSH, true, true, 2>(tmA, tmB, p, nullptr, st, 0)
+                 : launch_gemm<jsd::MODE_GRADPUSH, true, true, 1>(tmA, tmB, p, nullptr, st, 0);
+}
+
 int jsd_peer_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
-                          const float* gamma_dev, void* sk_workspace, jsd_stream_t stream) {
+                          const float* gamma_dev, int partials_bf16, jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_bwd_dv")) return rc;
-  (void)sk_workspace;                // the partial is read by the peers as one buffer: whole tiles only
+  if (partials_bf16) return peer_dv_push(Gmat, ldg, U, ctx, t_dev, gamma_dev, stream);
+  // fp32: the partial is read by the peers as one buffer: whole tiles only
   return dense_bwd_common(true, Gmat, ldg, U, ctx->rows, ctx->rows * ctx->world, ctx->dim, t_dev, gamma_dev, nullptr,
                           nullptr, stream, ctx, 0);
 }
 
 int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g, const void* U,
-                                const float* gdiag, const float* t_dev, const float* gamma_dev, void* dG,
-                                jsd_stream_t stream) {
+                                const float* gdiag, const float* t_dev, const float* gamma_dev, int partials_bf16,
+                                void* dG, jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_normalize_bwd_text")) return rc;
   JSD_REQUIRE(G && inv_g && U && gdiag && t_dev && dG, "jsd_peer_normalize_bwd_text: null pointer argument");
+  if (int rc = ensure_wait_cfg()) return rc;
   const int32_t* mine = ctx->flags[ctx->rank];
   jsd::NormBwdJob job{};
   job.X[0] = G;
@@ -796,8 +895,13 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
   job.partner_offset[0] = 0;
   job.dX[0] = dG;
   job.acc_slots = ctx->world;
-  for (int q = 0; q < ctx->world; ++q)        // rank q's partial, rows of this rank
-    job.slot[q] = (const float*)ctx->stage[q] + (size_t)ctx->rank * ctx->rows * ctx->dim;
+  job.slot_bf16 = partials_bf16 ? 1 : 0;
+  for (int q = 0; q < ctx->world; ++q) {
+    if (partials_bf16)      // rank q's partial for this rank's rows was pushed into slot q of the LOCAL buffer
+      job.slot[q] = (const float*)((const __nv_bfloat16*)ctx->stage[ctx->rank] + (size_t)q * ctx->rows * ctx->dim);
+    else                    // rank q's partial over all rows stays in rank q's memory: read this rank's rows of it
+      job.slot[q] = (const float*)ctx->stage[q] + (size_t)ctx->rank * ctx->rows * ctx->dim;
+  }
   job.wait_flags = mine + JSD_PEER_READY_DV;
   job.wait_counter = mine + JSD_PEER_COUNTER_DV;
   job.wait_count = ctx->world;
@@ -809,16 +913,16 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
 
 int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
                             const void* U, const float* inv_f, const float* inv_g, const void* Gmat, int64_t ldg,
-                            const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                            float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out,
-                            jsd_stream_t stream) {
+                            const float* gdiag, const float* t_dev, const float* gamma_dev, int partials_bf16,
+                            float* acc_u, float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG,
+                            float* dt_out, jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_backward")) return rc;
   JSD_REQUIRE(parity == 0 || parity == 1, "jsd_peer_dense_backward: parity must be 0 or 1");
   const void* V_all = ctx->v_all[parity][ctx->rank];
   const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim, off = ctx->rows * ctx->rank;
   cudaStream_t st = (cudaStream_t)stream;
-  // 1. the text-side partial first: its "complete" flag reaches the peers as early as possible
-  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, sk_workspace, stream)) return rc;
+  // 1. the text-side partial first: its "complete" flags reach the peers as early as possible
+  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, partials_bf16, stream)) return rc;
   SideStream* side = side_stream();
   if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
   // 2. the image-side contraction (split-K when a rank's rows underfill the GPU) ...
@@ -826,12 +930,14 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
   if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0,
                                 &su))
     return rc;
-  // 3. ... and NEXT TO it, on the helper stream, the text-side Jacobian: it waits for the peers' flags and pulls
-  //    their partials over NVLink (link-bound, needs few SMs: it runs on the CTA pairs the contraction leaves idle
-  //    and spreads out once that retires).  Enqueued after the contraction so that the latter gets its SMs first.
+  // 3. ... and NEXT TO it, on the helper stream, the text-side Jacobian: it waits for the peers' flags and sums
+  //    their partials (bf16: pushed into local slots while the peers' contractions ran; fp32: pulled over NVLink
+  //    now -- link-bound, it runs on the CTA pairs the contraction leaves idle and spreads out once that retires).
+  //    Enqueued after the contraction so that the latter gets its SMs first.
   cudaStream_t ts = side ? side->stream : st;
   if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  if (int rc = jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, dG, ts)) return rc;
+  if (int rc = jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, partials_bf16, dG, ts))
+    return rc;
   if (side) JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
   // 4. image-side Jacobian (+ gamma * dL_r/dt) behind the contraction
   if (int rc = normalize_bwd_impl(F, dtype, M, D, inv_f, acc_u, &su, V_all, off, gdiag, t_dev, gamma_dev, M, dF,
@@ -839,6 +945,22 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
     return rc;
   if (side) JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
   return 0;
+}
+
+/* ------------------------------------------------------------------ peer waits: time limit and error report */
+int jsd_peer_set_timeout(double seconds) {
+  JSD_REQUIRE(seconds > 0.0 && seconds < 1e7, "jsd_peer_set_timeout: seconds out of range");
+  g_wait_timeout_s = seconds;
+  g_wait_cfg_mask = 0;                // re-install on every device at its next peer call
+  return 0;
+}
+
+int jsd_peer_wait_error(int* kind, int* index, int* target) {
+  if (g_wait_err_host == nullptr || g_wait_err_host[0] == 0) return 0;
+  if (kind) *kind = g_wait_err_host[0];
+  if (index) *index = g_wait_err_host[1];
+  if (target) *target = g_wait_err_host[2];
+  return 1;
 }
 
 /* ------------------------------------------------------------------ device-side event trace */

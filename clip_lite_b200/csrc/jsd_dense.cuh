@@ -60,8 +60,11 @@ constexpr int MAX_PEERS = 8;                          // GPUs of one NVSwitch do
 // per-CTA shared-memory budget as a function of the CTA-group size (1 = single CTA, 2 = CTA pair)
 __host__ __device__ constexpr int b_rows_per_cta(int cg) { return BLOCK_N / cg; }
 __host__ __device__ constexpr int stage_bytes(int cg) { return A_TILE_BYTES + b_rows_per_cta(cg) * BLOCK_K * 2; }
-// the forward kernel gives 64 KB to the Gmat staging boxes of its 16 epilogue warps (TMA stores)
-__host__ __device__ constexpr int g_staging_bytes(int mode) { return mode == 0 ? NUM_EPI_WARPS * G_STAGE_BYTES : 0; }
+// the forward kernel gives 64 KB to the Gmat staging boxes of its 16 epilogue warps (TMA stores); so does the
+// GRADPUSH variant of the backward contraction, whose bf16 output tiles leave by TMA stores into PEER memory
+__host__ __device__ constexpr int g_staging_bytes(int mode) {
+  return (mode == 0 || mode == 3) ? NUM_EPI_WARPS * G_STAGE_BYTES : 0;
+}
 // k-atoms (64-wide, one 128B swizzle row each) staged per pipeline slot, and slots per ring
 #ifndef JSD_GRAD_KATOMS
 #define JSD_GRAD_KATOMS 2   // two k-atoms per slot: half as many barrier round trips per MMA (measured +3.6 %)
@@ -69,16 +72,19 @@ __host__ __device__ constexpr int g_staging_bytes(int mode) { return mode == 0 ?
 #ifndef JSD_GRAD_STAGES
 #define JSD_GRAD_STAGES 3
 #endif
-__host__ __device__ constexpr int k_atoms(int mode) { return mode == 0 ? 1 : JSD_GRAD_KATOMS; }
+__host__ __device__ constexpr int k_atoms(int mode) { return (mode == 0 || mode == 3) ? 1 : JSD_GRAD_KATOMS; }
 __host__ __device__ constexpr int num_stages(int cg, int mode) {
-  return mode == 0 ? (cg == 2 ? 5 : 3) : (cg == 2 ? JSD_GRAD_STAGES : 4 / JSD_GRAD_KATOMS);
+  return (mode == 0 || mode == 3) ? (cg == 2 ? 5 : 3) : (cg == 2 ? JSD_GRAD_STAGES : 4 / JSD_GRAD_KATOMS);
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int cg, int mode) {
   return num_stages(cg, mode) * k_atoms(mode) * stage_bytes(cg) + g_staging_bytes(mode) + 1024 /* align slack */ +
          256 /* barriers */;
 }
 
-enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1, MODE_SCORE = 2 };   // SCORE shares GRAD's pipeline shape
+// SCORE shares GRAD's pipeline shape; GRADPUSH is GRAD with the forward's shared-memory budget (one k-atom per
+// slot + 64 KB of store staging): out = bf16(gscale * acc), pushed tile by tile into the owner rank's memory
+enum GemmMode { MODE_FWD = 0, MODE_GRAD = 1, MODE_SCORE = 2, MODE_GRADPUSH = 3 };
+__host__ __device__ constexpr bool is_grad_mode(int mode) { return mode == MODE_GRAD || mode == MODE_GRADPUSH; }
 
 struct GemmParams {
   alignas(64) CUtensorMap tmG;   // FWD: Gmat [M, N] bf16 as the target of the epilogue's TMA stores (box 64 x 32)
@@ -86,6 +92,8 @@ struct GemmParams {
   int N;            // cols of the output tile space (FWD: text rows;  GRAD: D)
   int K;            // contraction length
   int n_fastest;    // tile order: 1 = consecutive tiles walk N first (A tile shared through L2)
+  int m_rot, n_rot; // the walk starts at this m-block / n-block (rotation): a peer forward starts on its OWN column
+                    // block (no exchange needed), a pushing dV contraction on the rows of the NEXT rank
   // FWD
   int row_offset;   // column of the positive of local row 0
   const float* t_dev;
@@ -129,13 +137,23 @@ struct GemmParams {
   // reached *wait_counter (the gathered B operand was written by peer GPUs).  peer_*: the output of a GRAD launch
   // is read by the other ranks straight out of this GPU's memory; the last CTA of the launch bumps *peer_counter
   // and publishes it to every rank's flag (system scope) once all CTAs' stores are fenced.
-  const int* wait_flags;
+  const int* wait_flags;         // FWD: [wait_count] one flag per source rank
   const int* wait_counter;
   int wait_count;
+  int wait_rows;                 // FWD: B rows (columns of S) owned by each source rank; a tile waits only for the
+                                 // ranks whose rows it loads (0: wait for every rank before the first load)
   int peer_world;                // 0 = nobody to notify
   int* peer_flag_dst[MAX_PEERS];
   int* peer_counter;
   int* peer_ticket;
+  // GRADPUSH: the [M, N] output is cut into `peer_world` row blocks of push_rows rows; block q belongs to rank q
+  // and is written there (tmPush[q]: [push_rows, N] bf16 in rank q's memory, box 64 x 32) by one TMA store per
+  // epilogue warp and tile.  push_ticket[q] counts the completed boxes of block q; the warp that completes the
+  // last one (push_expected of them) publishes *peer_counter + 1 to peer_flag_dst[q].
+  int push_rows;
+  int push_expected;
+  int* push_ticket;
+  alignas(64) CUtensorMap tmPush[MAX_PEERS];
 };
 
 // Score of a masked (out-of-range) pair: tau * kMaskedScore is finite and so negative that
@@ -289,13 +307,18 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k = (p.K + CHUNK_K - 1) / CHUNK_K;
+  constexpr bool IS_GRAD = is_grad_mode(MODE);
+  constexpr bool PUSH = MODE == MODE_GRADPUSH;
   const bool stream_k = (MODE == MODE_GRAD) && p.stream_k != 0;
 
-  constexpr int TRACE_ID = MODE == MODE_FWD ? TK_FWD : (MODE == MODE_GRAD ? TK_GRAD : TK_SCORE);
+  constexpr int TRACE_ID = MODE == MODE_FWD ? TK_FWD : (IS_GRAD ? TK_GRAD : TK_SCORE);
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(TRACE_ID, TE_START);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (MODE == MODE_FWD) {
+      if (p.gmat != nullptr) tma_prefetch_desc(&p.tmG);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -332,6 +355,10 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       n_blk = tile / num_m_blocks;
       m_blk = tile - n_blk * num_m_blocks;
     }
+    m_blk += p.m_rot;                       // rotations (< the block counts; 0 outside the peer paths)
+    if (m_blk >= num_m_blocks) m_blk -= num_m_blocks;
+    n_blk += p.n_rot;
+    if (n_blk >= num_n_blocks) n_blk -= num_n_blocks;
   };
 
   if (warp == 0) {
@@ -345,11 +372,19 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (CG == 2) tma_load_2d_pair(dst, m, full0 + 8u * s, c0, c1);
         else tma_load_2d(dst, m, full0 + 8u * s, c0, c1);
       };
+      // The B operand of a peer forward is gathered by the other GPUs writing into this GPU's memory, one flag per
+      // source rank ("my rows are in").  A tile waits only for the ranks whose rows it is about to load, so the walk
+      // (rotated to start on this rank's own column block) consumes the peers' rows in the order they land.
+      uint32_t peers_in = 0;
+      int wait_target = 0;
       if (p.wait_flags != nullptr) {
-        // the B operand was gathered by peer GPUs writing into this GPU's memory: wait for their "rows are in" flags
-        wait_flags_sys(p.wait_flags, p.wait_count, *p.wait_counter);
-        fence_proxy_async_all();
-        if (blockIdx.x == 0) trace_event(TRACE_ID, TE_PEERS_IN);
+        wait_target = *p.wait_counter;
+        if (p.wait_rows <= 0) {
+          wait_flags_sys(p.wait_flags, p.wait_count, wait_target, WAIT_GATHERED_ROWS);
+          fence_proxy_async_all();
+          peers_in = 0xFFFFFFFFu;
+          if (blockIdx.x == 0) trace_event(TRACE_ID, TE_PEERS_IN);
+        }
       }
       SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
       int tile, k0, k1;
@@ -358,6 +393,23 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * TILE_M + rank * BLOCK_M;     // this CTA's A rows
         const int n0 = n_blk * BLOCK_N + rank * BN_CTA;     // this CTA's share of the B rows
+        if constexpr (MODE == MODE_FWD) {
+          if (p.wait_flags != nullptr && peers_in != 0xFFFFFFFFu && n0 < p.N) {
+            const int q_lo = n0 / p.wait_rows;
+            const int q_hi = (min(n0 + BN_CTA, p.N) - 1) / p.wait_rows;
+            bool waited = false;
+            for (int q = q_lo; q <= q_hi && q < p.wait_count; ++q)
+              if (!((peers_in >> q) & 1u)) {
+                wait_flag_sys(p.wait_flags, q, wait_target, WAIT_GATHERED_ROWS);
+                peers_in |= 1u << q;
+                waited = true;
+              }
+            if (waited) {
+              fence_proxy_async_all();      // flag observed (generic proxy) before the TMA (async proxy) reads
+              if (blockIdx.x == 0 && peers_in == (1u << p.wait_count) - 1u) trace_event(TRACE_ID, TE_PEERS_IN);
+            }
+          }
+        }
         for (int kc = k0; kc < k1; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES * CG);
@@ -457,6 +509,21 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       gscale = gamma * (p.t_dev ? expf(*p.t_dev) : 1.f) * p.scale;
     }
     float pos_sum = 0.f, relu_sum = 0.f, lg_sum = 0.f;   // sum softplus(-x_pos), sum max(s,0), sum log2(1+e)
+    // GRADPUSH: owner rank of the box this warp stored last (its completion is counted before the staging box is
+    // re-used).  One lane: wait until the bulk store has been WRITTEN (not merely read), make it visible system-wide,
+    // count it; whoever completes an owner's block publishes "rank r's partial for you is complete" to that owner.
+    [[maybe_unused]] int pend_owner = -1;
+    [[maybe_unused]] auto push_signal = [&](int owner) {
+      tma_store_wait_all();
+      fence_proxy_async_all();
+      __threadfence_system();
+      if (atomicAdd(p.push_ticket + owner, 1) == p.push_expected - 1) {
+        __threadfence_system();
+        const int e = *reinterpret_cast<volatile int*>(p.peer_counter) + 1;
+        p.push_ticket[owner] = 0;                  // every box of this block has been counted: re-arm
+        st_release_sys(p.peer_flag_dst[owner], e);
+      }
+    };
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -498,7 +565,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #ifndef JSD_GRAD_EPI_SLEEP_NS
 #define JSD_GRAD_EPI_SLEEP_NS 1000
 #endif
-      if constexpr (MODE == MODE_GRAD && JSD_GRAD_EPI_SLEEP_NS > 0) {
+      if constexpr (IS_GRAD && JSD_GRAD_EPI_SLEEP_NS > 0) {
         mbar_wait_relaxed(tfull_bar(acc), acc_phase, JSD_GRAD_EPI_SLEEP_NS);   // long wait: poll gently
       } else {
         mbar_wait(tfull_bar(acc), acc_phase);   // short waits: all lanes poll (4 % faster than one lane + __syncwarp)
@@ -648,6 +715,19 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               st_shared_u16(row_base + piece * 16 + (dj & 7) * 2, 0);
             }
           }
+        } else if constexpr (PUSH) {
+          // bf16(gscale * acc) into this warp's staging box (same swizzled layout as the forward's Gmat box)
+          uint32_t packed[CW / 2];
+#pragma unroll
+          for (int j = 0; j < CW; j += 2)
+            packed[j >> 1] = pack_bf16x2(__uint_as_float(v[j]) * gscale, __uint_as_float(v[j + 1]) * gscale);
+          const uint32_t row_base = g_stage + lane * 128;
+#pragma unroll
+          for (int k4 = 0; k4 < CW / 8; ++k4) {
+            const uint32_t piece = (uint32_t)((CW / 8) * c + k4) ^ (uint32_t)(lane & 7);
+            st_shared_v4(row_base + piece * 16, packed[4 * k4], packed[4 * k4 + 1], packed[4 * k4 + 2],
+                         packed[4 * k4 + 3]);
+          }
         } else {
           const long long slot_off = (long long)row_in_tile * BLOCK_N + col_in_tile;
           if (sk_partial) {
@@ -702,6 +782,11 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
         }
       }
+      if constexpr (PUSH) {            // the previous tile's box has landed in its owner's memory: count it
+        if (pend_owner >= 0 && lane == 0) push_signal(pend_owner);
+        pend_owner = -1;
+        __syncwarp();
+      }
       uint32_t ra[CW], rb[CW];
       tmem_ld_chunk<CW>(t_base, ra);
 #pragma unroll 1
@@ -734,6 +819,19 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+      if constexpr (PUSH) {
+        fence_proxy_async();           // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        const int box_row = m0 + 32 * q, box_col = n0 + cgrp * COLS_PER_WARP;
+        if (box_row < p.M && box_col < p.N) {
+          const int owner = box_row / p.push_rows;
+          if (lane == 0) {
+            tma_store_2d(&p.tmPush[owner], g_stage, box_col, box_row - owner * p.push_rows);
+            tma_store_commit();
+          }
+          pend_owner = owner;
+        }
+      }
       if constexpr (MODE == MODE_SCORE) {
         if (row_ok && p.score_pass == 1) {
           if (sc_cnt > 0) atomicAdd(p.cnt_row + grow, sc_cnt);
@@ -759,6 +857,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     if constexpr (MODE == MODE_GRAD) {
       if (p.peer_world > 0) __threadfence_system();   // this thread's stores, before the CTA takes its ticket
+    }
+    if constexpr (PUSH) {
+      if (pend_owner >= 0 && lane == 0) push_signal(pend_owner);
     }
     if constexpr (MODE == MODE_FWD) {
       if (p.gmat != nullptr && lane == 0) tma_store_wait_all();   // smem must outlive the last store
@@ -787,21 +888,33 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if constexpr (MODE != MODE_FWD) {
     if (blockIdx.x == 0 && threadIdx.x == 0) trace_event(TRACE_ID, TE_END);   // block 0's end (no last-CTA ticket here)
   }
-  if constexpr (MODE == MODE_GRAD) {
-    // Peer exchange: once every CTA's stores are fenced, the last CTA publishes "this rank's partial is complete".
+  if constexpr (IS_GRAD) {
+    // Peer exchange.  fp32 route: once every CTA's stores are fenced, the last CTA publishes "this rank's partial
+    // is complete" -- one thread per destination, so that the remote release-stores (each a ~2 us round trip) go
+    // out together instead of one after the other.  GRADPUSH: the flags went out per owner block already; the
+    // last CTA only advances the launch counter they were derived from.
     if (p.peer_world > 0) {
-      int* s_last = reinterpret_cast<int*>(smem_raw);
+      volatile int* s_last = reinterpret_cast<volatile int*>(smem_raw);
       if (threadIdx.x == 0) {
         __threadfence_system();
-        *s_last = (atomicAdd(p.peer_ticket, 1) == (int)gridDim.x - 1);
+        s_last[0] = (atomicAdd(p.peer_ticket, 1) == (int)gridDim.x - 1);
       }
       __syncthreads();
-      if (*s_last && threadIdx.x == 0) {
-        __threadfence_system();
-        const int e = *p.peer_counter + 1;
-        *p.peer_counter = e;
-        for (int q = 0; q < p.peer_world; ++q) st_release_sys(p.peer_flag_dst[q], e);
-        *p.peer_ticket = 0;
+      if (s_last[0]) {
+        if (threadIdx.x == 0) {
+          __threadfence_system();
+          const int e = *p.peer_counter + 1;
+          *p.peer_counter = e;
+          s_last[1] = e;
+          *p.peer_ticket = 0;
+        }
+        __syncthreads();
+        if constexpr (!PUSH) {
+          if ((int)threadIdx.x < p.peer_world) {
+            __threadfence_system();
+            st_release_sys(p.peer_flag_dst[threadIdx.x], s_last[1]);
+          }
+        }
       }
     }
   }

@@ -139,20 +139,45 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
-// Spin until every flag[0..count) has reached `target` (flags only grow); traps after 20 s instead of hanging.
-__device__ __forceinline__ void wait_flags_sys(const int* flags, int count, int target) {
-  for (int i = 0; i < count; ++i) {
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    while (ld_acquire_sys(flags + i) - target < 0) {
-      if ((++spins & 0xFFu) == 0) {
-        __nanosleep(200);
-        const uint64_t now = global_timer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 20000000000ull) __trap();
-      }
+// Peer waits are bounded: a rank that never publishes (crashed, or more than the timeout behind -- a dataloader
+// respawn, a checkpoint write outside any barrier) must not hang the GPU forever.  The limit is a library parameter
+// (jsd_peer_set_timeout / JSD_PEER_TIMEOUT_S, default 300 s, NCCL-like), and on expiry the waiting thread first
+// records WHICH flag it was waiting for in a host-mapped error word -- readable by the host even after the trap
+// has poisoned the context (jsd_peer_wait_error) -- and only then traps.
+struct WaitCfg {
+  unsigned long long timeout_ns;
+  int* err_host;                // mapped pinned host memory (may be null): [0] = code, [1] = flag index, [2] = target
+};
+__device__ WaitCfg g_wait_cfg = {300000000000ull, nullptr};
+enum WaitKind { WAIT_GATHERED_ROWS = 1, WAIT_GRAD_PARTIALS = 2 };
+
+__device__ __noinline__ void wait_timed_out(int kind, int index, int target) {
+  int* e = g_wait_cfg.err_host;
+  if (e != nullptr) {
+    e[1] = index;
+    e[2] = target;
+    __threadfence_system();
+    e[0] = kind;
+    __threadfence_system();
+  }
+  __trap();
+}
+// Spin until flags[i] has reached `target` (flags only grow).
+__device__ __forceinline__ void wait_flag_sys(const int* flags, int i, int target, int kind) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (ld_acquire_sys(flags + i) - target < 0) {
+    if ((++spins & 0xFFu) == 0) {
+      __nanosleep(200);
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > g_wait_cfg.timeout_ns) wait_timed_out(kind, i, target);
     }
   }
+}
+// ... until every flag[0..count) has
+__device__ __forceinline__ void wait_flags_sys(const int* flags, int count, int target, int kind) {
+  for (int i = 0; i < count; ++i) wait_flag_sys(flags, i, target, kind);
 }
 
 // ---------------------------------------------------------------- TMA

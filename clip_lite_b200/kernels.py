@@ -111,22 +111,49 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
 # ------------------------------------------------------------------ dense mode
 # Scratch buffers of the dense path, one of each per DEVICE, allocated zeroed on first use and kept: the kernels
 # leave their flag / ticket words zero after every launch.  They are deliberately not per stream -- a CUDA-graph
-# capture must not allocate (and memset) 33 MB inside the graph, it re-uses the buffers of the eager warm-up --
-# so at most one dense step may be in flight per device at a time (steps on one stream, or graph replays, are).
+# capture must not allocate (and memset) 42 MB inside the graph, it re-uses the buffers of the eager warm-up --
+# so at most one dense step may be in flight per device at a time.  That rule is ENFORCED, not just documented:
+# when a different stream than the last user asks for the buffers, it is first made to wait for that stream
+# (two loss modules on two streams, or per-device threads, are serialised instead of sharing tickets and partial
+# sums), and a failing library call re-zeroes the ticket words (an aborted launch may have left them armed).
 _SK_WORKSPACES = {}
 _FWD_WORKSPACES = {}
+_LAST_STREAM = {}
 
 
 def _device_workspace(cache: dict, nbytes: int, device) -> torch.Tensor:
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     ws = cache.get(key)
+    capturing = torch.cuda.is_current_stream_capturing()
     if ws is None:
-        if torch.cuda.is_current_stream_capturing():
+        if capturing:
             raise RuntimeError("run one eager step of the dense path before capturing it into a CUDA graph "
                                "(its scratch buffers are allocated on first use)")
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         cache[key] = ws
+    if not capturing:                  # inside a capture the graph's own edges order the kernels
+        cur = torch.cuda.current_stream(ws.device)
+        last = _LAST_STREAM.get(key)
+        if last is not None and last != cur:
+            cur.wait_stream(last)
+        _LAST_STREAM[key] = cur
     return ws
+
+
+def _rearm_workspaces() -> None:
+    """After a failed library call: zero the "last block" tickets and hand-off flags of every cached scratch buffer
+    (an aborted launch sequence may have left them armed, which would corrupt every later step)."""
+    try:
+        flag_bytes = _lib.load().jsd_streamk_flag_bytes()
+        for ws in _FWD_WORKSPACES.values():
+            ws[:16].zero_()
+        for ws in _SK_WORKSPACES.values():
+            ws[:flag_bytes].zero_()
+    except Exception:
+        pass                           # the context may be gone; the original error is what matters
+
+
+_lib.ERROR_HOOKS.append(_rearm_workspaces)
 
 
 def streamk_workspace(device) -> torch.Tensor:

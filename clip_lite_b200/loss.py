@@ -146,7 +146,10 @@ class JSDInfoMaxLoss(nn.Module):
     Extra keyword-only options (defaults reproduce the reference):
       neg_mode  "shift1": one negative per row, the text batch rolled by one
                 (reference semantics, HBM-bound fused kernel);
-                "dense": every off-diagonal pair is a negative (tensor-core kernels).
+                "dense": every off-diagonal pair is a negative (tensor-core kernels).  On a cluster-
+                mode call (neg_image_features / neg_text_features given) the estimator runs over
+                the concatenated 2B' rows, so each image row sees every other text row -- the B'
+                hard negatives included -- as a negative (tested against the oracle).
       gather    with neg_mode="dense": each rank scores its rows against the text
                 embeddings of every rank of ``process_group`` (gradients of the text
                 side are summed back on the owning rank).

@@ -5,12 +5,14 @@ every rank's dV partial has to be summed on the rank owning the text rows (reduc
 fused into the kernels on either side of them instead of being NCCL collectives:
 
   normalise + gather   the normalise kernel stores each bf16 text row into EVERY rank's gathered V buffer
-                       (peer stores over NVLink) and publishes a flag; the forward's TMA producer waits for
-                       the flags of all ranks before its first load.
-  dV + reduce          the dV contraction leaves its fp32 partial (all text rows) in a peer-mapped buffer and
-                       publishes a flag; the owner's text-side Jacobian kernel waits for all flags, reads its
-                       rows of every rank's partial over NVLink (coalesced 512-byte row segments) and sums them
-                       in rank order (deterministic).
+                       (peer stores over NVLink), one destination after the other with one flag each; the
+                       forward starts on its own column block and every tile waits only for the ranks whose
+                       rows it loads, so the exchange runs underneath the forward.
+  dV + reduce          ``partials="bf16"`` (default): the dV contraction's epilogue pushes every output tile as
+                       bf16 by TMA store into the OWNER's slot buffer (one flag per owner) -- the traffic hides
+                       behind the contraction; the owner's text-side Jacobian waits for all flags and sums the
+                       world slots in rank order (deterministic).  ``partials="fp32"``: the contraction leaves an
+                       fp32 partial in its own peer-mapped buffer and the owners pull their rows over NVLink.
 
 A step is therefore five kernel launches and no collective call, which also makes the whole step
 capturable in a CUDA graph (``PeerGraphedStep``).  ``torch.distributed`` is used once, at set-up, to
@@ -19,6 +21,7 @@ exchange the CUDA IPC handles of the buffers.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -66,9 +69,16 @@ class PeerExchange:
     """Buffers, flags and peer mappings for a fixed (rows per rank, D) on a process group of <= 8 GPUs of one
     NVSwitch domain.  Collective constructor: every rank of ``group`` must create it at the same time."""
 
-    def __init__(self, rows: int, dim: int, group=None):
+    def __init__(self, rows: int, dim: int, group=None, partials: Optional[str] = None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        partials = partials or os.environ.get("JSD_PEER_PARTIALS", "bf16")
+        if partials not in ("bf16", "fp32"):
+            raise ValueError(f"partials must be 'bf16' or 'fp32', got {partials!r}")
+        if partials == "bf16" and rows % 32:
+            partials = "fp32"              # the pushed boxes are 32 rows tall and must not straddle two owners
+        self.partials = partials
+        self._bf16 = int(partials == "bf16")
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > _lib.MAX_PEERS:
@@ -113,6 +123,19 @@ class PeerExchange:
         for key in [k for k, v in _EXCHANGES.items() if v is self]:
             del _EXCHANGES[key]
 
+    @staticmethod
+    def wait_error() -> Optional[str]:
+        """Readable report of an expired peer wait of this process (None if there is none).  The kernels trap
+        after `jsd_peer_set_timeout` seconds without progress, which poisons the CUDA context; the reason is kept
+        in host memory and can still be read here (e.g. from an except handler around the failing sync)."""
+        kind, index, target = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        if not _lib.load().jsd_peer_wait_error(ctypes.byref(kind), ctypes.byref(index), ctypes.byref(target)):
+            return None
+        what = {1: "the forward kernel waited for the text rows of", 2: "the text-side Jacobian waited for the "
+                "gradient partial of"}.get(kind.value, "a kernel waited for")
+        return (f"peer exchange timed out: {what} rank {index.value} (step count {target.value}) -- that rank never "
+                f"published it; the ranks must stay in lock step within the wait limit (jsd_peer_set_timeout)")
+
     # ------------------------------------------------------------------ the four fused launches
     def normalize_push(self, f: torch.Tensor, g: torch.Tensor, parity: int):
         """(U, inv_f, inv_g); V rows land in every rank's v_all[parity]."""
@@ -142,7 +165,7 @@ class PeerExchange:
     def dense_bwd_dv(self, gmat: torch.Tensor, u: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor):
         tt, gg = K._scalar(t, "temperature"), K._scalar(gamma, "gamma")
         _lib.call("jsd_peer_dense_bwd_dv", gmat.data_ptr(), gmat.shape[1], u.data_ptr(), self._ctx_ptr,
-                  tt.data_ptr(), gg.data_ptr(), K.streamk_workspace(gmat.device).data_ptr(), K._stream())
+                  tt.data_ptr(), gg.data_ptr(), self._bf16, K._stream())
 
     def dense_backward(self, f, g, t, gamma, parity: int, u, inv_f, inv_g, gmat, gdiag):
         """Whole backward of a step in one library call.  Returns (dF, dG, dt)."""
@@ -154,7 +177,7 @@ class PeerExchange:
         ws = K.dense_workspace(f.device)
         _lib.call("jsd_peer_dense_backward", f.data_ptr(), g.data_ptr(), K._code(f), self._ctx_ptr, parity,
                   u.data_ptr(), inv_f.data_ptr(), inv_g.data_ptr(), gmat.data_ptr(), gmat.shape[1], gdiag.data_ptr(),
-                  tt.data_ptr(), gg.data_ptr(), acc.data_ptr(), small.data_ptr(), ws.data_ptr(),
+                  tt.data_ptr(), gg.data_ptr(), self._bf16, acc.data_ptr(), small.data_ptr(), ws.data_ptr(),
                   K.streamk_workspace(f.device).data_ptr(), df.data_ptr(), dg.data_ptr(), small[m:].data_ptr(),
                   K._stream())
         return df, dg, small[m]
@@ -163,20 +186,22 @@ class PeerExchange:
         tt, gg = K._scalar(t, "temperature"), K._scalar(gamma, "gamma")
         dg = torch.empty_like(g)
         _lib.call("jsd_peer_normalize_bwd_text", g.data_ptr(), K._code(g), self._ctx_ptr, inv_g.data_ptr(),
-                  u.data_ptr(), gdiag.data_ptr(), tt.data_ptr(), gg.data_ptr(), dg.data_ptr(), K._stream())
+                  u.data_ptr(), gdiag.data_ptr(), tt.data_ptr(), gg.data_ptr(), self._bf16, dg.data_ptr(), K._stream())
         return dg
 
 
 _EXCHANGES = {}
 
 
-def get_exchange(rows: int, dim: int, group=None, tag: str = "text") -> PeerExchange:
-    """Cached PeerExchange per (group, rows, D, tag); the first call is collective.  ``tag`` names independent
-    exchanges of the same shape (the symmetric route gathers the image rows through a second one)."""
-    key = (id(group) if group is not None else 0, rows, dim, torch.cuda.current_device(), tag)
+def get_exchange(rows: int, dim: int, group=None, tag: str = "text", partials: Optional[str] = None) -> PeerExchange:
+    """Cached PeerExchange per (group, rows, D, tag, partials); the first call is collective.  ``tag`` names
+    independent exchanges of the same shape (the symmetric route gathers the image rows through a second one).
+    ``partials`` ("bf16" / "fp32", default: environment JSD_PEER_PARTIALS or "bf16") must agree on all ranks."""
+    partials = partials or os.environ.get("JSD_PEER_PARTIALS", "bf16")
+    key = (id(group) if group is not None else 0, rows, dim, torch.cuda.current_device(), tag, partials)
     ex = _EXCHANGES.get(key)
     if ex is None:
-        ex = _EXCHANGES[key] = PeerExchange(rows, dim, group)
+        ex = _EXCHANGES[key] = PeerExchange(rows, dim, group, partials=partials)
     return ex
 
 
@@ -281,10 +306,10 @@ class PeerGraphedStep:
     double-buffered gathered V, and replayed alternately.  Returns static tensors (loss, dF, dG, dt)."""
 
     def __init__(self, f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group=None, warmup: int = 2,
-                 route: str = "reduce"):
+                 route: str = "reduce", partials: Optional[str] = None):
         if route not in ("reduce", "symmetric"):
             raise ValueError(f"route must be 'reduce' or 'symmetric', got {route!r}")
-        self.ex = get_exchange(f.shape[0], f.shape[1], group)
+        self.ex = get_exchange(f.shape[0], f.shape[1], group, partials=partials)
         ex_u = get_exchange(f.shape[0], f.shape[1], group, tag="image") if route == "symmetric" else None
         self.f = f.detach().clone()
         self.g = g.detach().clone()

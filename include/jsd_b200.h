@@ -161,37 +161,48 @@ int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N
  * One process per GPU; the two exchange steps of the sharded path (all-gather of the text rows, sum of
  * the dV partials on the owner rank) are fused into the kernels that produce / consume the data, over NVLink peer
  * memory, instead of separate NCCL collectives:
- *   jsd_peer_normalize_push      normalises F -> local U, G -> V rows stored into EVERY rank's gathered V buffer
- *   jsd_peer_dense_fwd           jsd_dense_fwd on (U, this rank's gathered V); its TMA producer first waits for
- *                                every rank's "rows are in" flag
- *   jsd_peer_dense_bwd_dv        dV partial over all text rows into this rank's peer-mapped buffer; its last
- *                                CTA publishes "partial complete" to every rank
- *   jsd_peer_normalize_bwd_text  waits for every rank's flag, reads its rows of every rank's partial over NVLink
- *                                and sums them in rank order (deterministic): the reduce-scatter is fused into
- *                                its consumer; then positive-pair term and Jacobian of F.normalize
+ *   jsd_peer_normalize_push      normalises F -> local U, G -> V rows stored into EVERY rank's gathered V buffer,
+ *                                one destination after the other (itself, rank - 1, rank - 2, ...), each with its
+ *                                own "rows of rank r are in" flag as soon as all of its rows have landed
+ *   jsd_peer_dense_fwd           jsd_dense_fwd on (U, this rank's gathered V); the walk starts on the rank's own
+ *                                column block and every tile waits only for the flags of the ranks whose rows it
+ *                                loads, so the blocks are consumed in the order they arrive (rank, rank + 1, ...)
+ *   jsd_peer_dense_bwd_dv        dV partial over all text rows.  partials_bf16 = 1: the contraction's epilogue
+ *                                pushes every output tile as bf16 by TMA store into its OWNER's slot buffer (owner
+ *                                blocks walked from rank + 1 on, one flag per owner) -- the reduce-scatter's traffic
+ *                                is hidden behind the contraction; partials_bf16 = 0: the fp32 partial stays in this
+ *                                rank's peer-mapped buffer and the last CTA publishes "complete" to every rank
+ *   jsd_peer_normalize_bwd_text  waits for every rank's flag, sums the world partials of its rows in rank order
+ *                                (deterministic; bf16: from its local slots, fp32: read over NVLink), then
+ *                                positive-pair term and Jacobian of F.normalize
  * (the image side uses jsd_dense_backward_image_side with V_all = v_all[parity][rank]).
  * Buffers come from jsd_peer_alloc (cudaMalloc, zero-filled) and are mapped into the other processes with
  * jsd_peer_export / jsd_peer_open (CUDA IPC).  The gathered V buffer is double-buffered by the step's parity
  * (the caller alternates 0, 1, 0, ...; every rank must use the same sequence), so a rank may start pushing step
  * k+1 while a slower rank still reads step k.  Flags only grow (per-buffer push counters): nothing is reset.
- * Every rank must make the same sequence of calls (collective semantics), one step in flight at a time. */
+ * Every rank must make the same sequence of calls (collective semantics), one step in flight at a time, and the
+ * ranks must stay within the wait limit of each other (jsd_peer_set_timeout, default 300 s): a wait that expires
+ * records which flag it was waiting for (jsd_peer_wait_error) and traps. */
 #define JSD_MAX_PEERS 8
 #define JSD_PEER_HANDLE_BYTES 64
 /* layout of a rank's flag block (int32 words) */
 #define JSD_PEER_READY_V 0        /* [parity][source rank]: pushes of that rank into this rank's V buffer */
-#define JSD_PEER_READY_DV 16      /* [source rank]: dV partial launches of that rank */
+#define JSD_PEER_READY_DV 16      /* [source rank]: dV partial launches of that rank (for this rank's rows) */
 #define JSD_PEER_COUNTER_V 24     /* [parity] this rank's own push counter */
 #define JSD_PEER_COUNTER_DV 26
-#define JSD_PEER_TICKET_PUSH 27
-#define JSD_PEER_TICKET_DV 28
-#define JSD_PEER_FLAG_INTS 32
+#define JSD_PEER_TICKET_DV 28     /* CTAs of the dV launch that have finished */
+#define JSD_PEER_TICKET_PUSH 32   /* [destination slot]: blocks of the push kernel done with that destination */
+#define JSD_PEER_TICKET_DVPUSH 40 /* [owner rank]: output boxes of the dV launch landed at that owner */
+#define JSD_PEER_FLAG_INTS 64
 
 typedef struct jsd_peer_ctx {
   int32_t rank, world;
   int64_t rows;                          /* rows per rank (the same on every rank) */
   int64_t dim;                           /* D */
   void* v_all[2][JSD_MAX_PEERS];         /* [parity][q]: rank q's gathered V [world * rows, D] bf16, as mapped here */
-  void* stage[JSD_MAX_PEERS];            /* rank q's dV partial [world * rows, D] fp32, as mapped here */
+  void* stage[JSD_MAX_PEERS];            /* rank q's gradient staging, world * rows * D * 4 bytes, as mapped here:
+                                            fp32 route: rank q's own partial [world * rows, D] fp32;
+                                            bf16 route: [world][rows, D] bf16, slot s = the partial pushed by rank s */
   int32_t* flags[JSD_MAX_PEERS];         /* rank q's flag block, zero before the first step */
 } jsd_peer_ctx;
 
@@ -201,26 +212,32 @@ int jsd_peer_free(void* ptr);
 int jsd_peer_export(void* ptr, void* handle64);
 int jsd_peer_open(const void* handle64, void** out_ptr);
 int jsd_peer_close(void* ptr);
+/* Time limit of every wait on a peer's flag (seconds; default 300, or the environment variable JSD_PEER_TIMEOUT_S).
+ * jsd_peer_wait_error: non-zero iff a wait of this process has expired; kind 1 = a forward waiting for the text rows
+ * of rank *index, 2 = a text-side Jacobian waiting for the gradient partial of rank *index; *target = the step
+ * count it was waiting for.  The word lives in host memory: it can be read after the trap poisoned the context. */
+int jsd_peer_set_timeout(double seconds);
+int jsd_peer_wait_error(int* kind, int* index, int* target);
 int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity, void* U_bf16,
                             float* inv_f, float* inv_g, jsd_stream_t stream);
 int jsd_peer_dense_fwd(const void* U_bf16, const jsd_peer_ctx* ctx, int parity, const float* t_dev, void* Gmat_bf16,
                        int64_t ldg, float* gdiag, void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
 int jsd_peer_dense_bwd_dv(const void* Gmat_bf16, int64_t ldg, const void* U_bf16, const jsd_peer_ctx* ctx,
-                          const float* t_dev, const float* gamma_dev, void* sk_workspace, jsd_stream_t stream);
+                          const float* t_dev, const float* gamma_dev, int partials_bf16, jsd_stream_t stream);
 int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g,
                                 const void* U_bf16, const float* gdiag, const float* t_dev, const float* gamma_dev,
-                                void* dG, jsd_stream_t stream);
+                                int partials_bf16, void* dG, jsd_stream_t stream);
 
-/* Whole backward of a peer-exchange step in one call: the dV partial first (its flag goes out early), then the dU
+/* Whole backward of a peer-exchange step in one call: the dV partial first (its flags go out early), then the dU
  * contraction (split-K when the rank's rows underfill the GPU) with -- on a library-owned helper stream NEXT TO
- * it -- the text-side Jacobian that waits for the peers and pulls their partials over NVLink, then the image-side
+ * it -- the text-side Jacobian that waits for the peers and sums their partials, then the image-side
  * Jacobian (+ dt_out = gamma * dL_r/dt).  acc_u fp32 [rows, D] and rowdot fp32 [rows] are scratch; workspace =
  * the forward's; sk_workspace = jsd_streamk_workspace_bytes() bytes (split-K slices). */
 int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
                             const void* U_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16,
-                            int64_t ldg, const float* gdiag, const float* t_dev, const float* gamma_dev, float* acc_u,
-                            float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out,
-                            jsd_stream_t stream);
+                            int64_t ldg, const float* gdiag, const float* t_dev, const float* gamma_dev,
+                            int partials_bf16, float* acc_u, float* rowdot, void* workspace, void* sk_workspace,
+                            void* dF, void* dG, float* dt_out, jsd_stream_t stream);
 
 /* ------------------------------------------------------------------ retrieval / zero-shot scoring
  * replaces: retrieval.py:143 (`sims_matrix = image_embeds @ text_embeds.t()`, copied to the host) + the NumPy

@@ -142,6 +142,30 @@ def test_dense_equals_mean_over_shifts_of_the_reference_estimator(ops):
     assert relerr(dense[0], ops.jsd_index_loss(f, g, t)[1][0]) < LOSS_RTOL
 
 
+def test_cluster_batches_with_dense_negatives(L):
+    """neg_mode="dense" on a cluster-mode call (loss.py:225-252 inputs): the estimator runs over the concatenated
+    2B' rows with EVERY other text row -- the B' hard negatives included -- as a negative of each image row
+    ("dense + hard-negative columns", SURVEY 8-f #2).  Checked against oracle.jsd_dense on the concatenation."""
+    half, d = 96, 64
+    gen = torch.Generator().manual_seed(11)
+    img, txt, nimg, ntxt = (torch.randn(half, d, generator=gen) for _ in range(4))
+    m = L.JSDInfoMaxLoss(image_dim=d, text_dim=d, type="dot", image_prior=False, text_prior=False,
+                         neg_mode="dense").cuda()
+    m.global_d.img_block = torch.nn.Identity()
+    m.global_d.text_block = torch.nn.Identity()
+    leaves = [x.cuda().requires_grad_(True) for x in (img, txt, nimg, ntxt)]
+    out = m(image_features=leaves[0], text_features=leaves[1], neg_image_features=leaves[2],
+            neg_text_features=leaves[3])
+    out["total_loss"].backward()
+    f_all, g_all = torch.cat((img, nimg)).double(), torch.cat((txt, ntxt)).double()
+    ref = orc.jsd_dense(f_all, g_all, orc.T_INIT)
+    rdf, rdg, rdt = orc.jsd_dense_grads(f_all, g_all, orc.T_INIT, gamma=0.9)
+    assert relerr(out["cross_modal_loss"], ref["loss"]) < LOSS_RTOL
+    assert relerr(torch.cat((leaves[0].grad, leaves[2].grad)), rdf) < GRAD_RTOL
+    assert relerr(torch.cat((leaves[1].grad, leaves[3].grad)), rdg) < GRAD_RTOL
+    assert relerr(m.global_d.temperature.grad, rdt) < GRAD_RTOL
+
+
 def test_no_grad_forward_and_module_eval(L):
     m = L.JSDInfoMaxLoss(image_dim=32, text_dim=24, image_prior=True, text_prior=True, neg_mode="dense").cuda().eval()
     with torch.no_grad():

@@ -1,6 +1,9 @@
-"""Multi-GPU parity (NCCL): the gathered dense loss on R ranks equals the single-GPU dense
-loss on the concatenated batch (loss, dF, dG, dt), with the gradient convention of
-SURVEY 8e.  Skipped on boxes with fewer than two GPUs."""
+"""Multi-GPU parity: the sharded dense loss on R ranks equals the single-GPU dense loss on the concatenated
+batch (loss, dF, dG, dt), with the gradient convention of SURVEY 8e -- for every exchange (NCCL collectives,
+peer memory) x route (reduce with bf16 / fp32 partials, symmetric), at a small shape and at BASELINE configs[2]
+(global batch 8192, D = 1024).  The world-size-1 cases run the very same peer kernels (per-destination push
+flags, per-source forward waits, TMA-pushed bf16 partials) on ONE GPU, so the single-GPU test tier covers them;
+the others are skipped on boxes with fewer GPUs.  Tolerances: BASELINE.json (loss 1e-3, gradients 1e-2)."""
 import os
 import socket
 
@@ -13,7 +16,8 @@ from oracle import jsd_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-B, D = 1024, 256
+SHAPES = [(1024, 256), (8192, 1024)]
+SEEDS = (0, 1, 2)
 
 
 def _free_port():
@@ -24,182 +28,133 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, results):
-    from clip_lite_b200 import parallel
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
-        f, g = orc.synth_embeddings(B, D, seed=0, correlated=True)
-        m = B // world
-        fl = f[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
-        gl = g[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
-        t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
-        loss, _ = parallel.gathered_dense_loss(fl, gl, t)
-        (0.5 * loss).backward()
-        logged = parallel.global_loss_for_logging(loss)
-        torch.cuda.synchronize()
-        results[rank] = tuple(x.detach().cpu() for x in (loss, fl.grad, gl.grad, t.grad, logged))
-    finally:
-        dist.destroy_process_group()
+def _loss_fn(kind):
+    """kind -> f(fl, gl, t) returning the local loss."""
+    from clip_lite_b200 import parallel, peer
+    if kind == "nccl-reduce":
+        return lambda f, g, t: parallel.gathered_dense_loss(f, g, t)[0]
+    if kind == "nccl-symmetric":
+        return lambda f, g, t: parallel.gathered_dense_loss(f, g, t, route="symmetric")[0]
+    if kind in ("peer-bf16", "peer-fp32"):
+        part = kind.split("-")[1]
+        return lambda f, g, t: peer.peer_dense_loss(
+            f, g, t, exchange=peer.get_exchange(f.shape[0], f.shape[1], partials=part))[0]
+    if kind == "peer-symmetric":
+        return lambda f, g, t: peer.peer_dense_loss(f, g, t, route="symmetric")[0]
+    raise ValueError(kind)
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_gathered_dense_matches_single_gpu(world):
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    results = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
-    f, g = orc.synth_embeddings(B, D, seed=0, correlated=True)
-    fd, gd = f.double(), g.double()
-    full = orc.jsd_dense(fd, gd, orc.T_INIT)
-    df, dg, dt = orc.jsd_dense_grads(fd, gd, orc.T_INIT, gamma=0.5)
-    m = B // world
-    tot_dt = 0.0
-    for r in range(world):
-        loss, gf, gg, gt, logged = results[r]
-        slab = orc.jsd_dense(fd[r * m:(r + 1) * m], gd, orc.T_INIT, row_offset=r * m)
-        assert abs(float(loss) - float(slab["loss"])) < 1e-3 * float(slab["loss"])
-        assert abs(float(logged) - float(full["loss"])) < 1e-3 * float(full["loss"])
-        ref_f, ref_g = world * df[r * m:(r + 1) * m], world * dg[r * m:(r + 1) * m]
-        assert (gf.double() - ref_f).abs().max() < 1e-2 * ref_f.abs().max()
-        assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
-        tot_dt += float(gt)
-    assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
-
-
-# ------------------------------------------------------------------ peer-memory exchange (no NCCL on the data path)
-def _peer_worker(rank, world, port, results):
+def _worker(rank, world, port, results, kind, b, d):
     from clip_lite_b200 import peer
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        m = B // world
+        fn = _loss_fn(kind)
+        m = b // world
         t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
         out = []
         # three eager steps on different data (both parities of the double-buffered gathered V, flags re-used)
-        for seed in (0, 1, 2):
-            f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
+        for seed in SEEDS:
+            f, g = orc.synth_embeddings(b, d, seed=seed, correlated=True)
             fl = f[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
             gl = g[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
             t.grad = None
-            loss, _ = peer.peer_dense_loss(fl, gl, t)
+            loss = fn(fl, gl, t)
             (0.5 * loss).backward()
             torch.cuda.synchronize()
             out.append(tuple(x.detach().cpu() for x in (loss, fl.grad, gl.grad, t.grad)))
-        # forward only (no backward between two forwards) must not disturb the exchange
-        with torch.no_grad():
-            l_eval, _ = peer.peer_dense_loss(fl.detach(), gl.detach(), t.detach())
-            l_eval2, _ = peer.peer_dense_loss(fl.detach(), gl.detach(), t.detach())
-        torch.cuda.synchronize()
-        assert float(l_eval) == float(l_eval2) == float(out[-1][0])
-        # graphed replay: two graphs (one per parity), several replays on the seed-2 data, bit-identical to eager
-        gs = peer.PeerGraphedStep(fl.detach(), gl.detach(), t.detach())
-        gs.gamma.fill_(0.5)
-        for _ in range(5):
-            l2, df2, dg2, dt2 = gs()
-        torch.cuda.synchronize()
-        out.append(tuple(x.detach().cpu().clone() for x in (l2, df2, dg2, dt2)))
-        results[rank] = out
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_peer_exchange_matches_single_gpu(world):
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    results = mp.Manager().dict()
-    mp.spawn(_peer_worker, args=(world, _free_port(), results), nprocs=world, join=True)
-    m = B // world
-    for si, seed in enumerate((0, 1, 2)):
-        f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
-        fd, gd = f.double(), g.double()
-        df, dg, dt = orc.jsd_dense_grads(fd, gd, orc.T_INIT, gamma=0.5)
-        tot_dt = 0.0
-        for r in range(world):
-            loss, gf, gg, gt = results[r][si]
-            slab = orc.jsd_dense(fd[r * m:(r + 1) * m], gd, orc.T_INIT, row_offset=r * m)
-            assert abs(float(loss) - float(slab["loss"])) < 1e-3 * float(slab["loss"])
-            ref_f, ref_g = world * df[r * m:(r + 1) * m], world * dg[r * m:(r + 1) * m]
-            assert (gf.double() - ref_f).abs().max() < 1e-2 * ref_f.abs().max()
-            assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
-            tot_dt += float(gt)
-        assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
-    for r in range(world):      # graph replay == eager on the same data (deterministic kernels, fixed slot order)
-        for a, b in zip(results[r][2], results[r][3]):
-            assert torch.equal(a, b)
-
-
-# ------------------------------------------------------------------ "symmetric" route (no gradient traffic)
-# Host logic validated on CPU (tests/test_parallel_cpu.py, gloo, world 2 and 4); the kernels are the ones the
-# "reduce" route uses.  Written after the round's GPU budget was spent, so these multi-GPU checks are opt-in until
-# their first run: JSD_TEST_SYMMETRIC=1 python -m pytest tests/test_gpu_parallel.py -m gpu -k symmetric
-_SYMMETRIC = pytest.mark.skipif(os.environ.get("JSD_TEST_SYMMETRIC") != "1",
-                                reason="symmetric route not yet exercised on hardware (set JSD_TEST_SYMMETRIC=1)")
-
-
-def _symmetric_worker(rank, world, port, results, use_peer):
-    from clip_lite_b200 import parallel, peer
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
-        m = B // world
-        t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
-        out = []
-        for seed in (0, 1, 2):
-            f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
-            fl = f[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
-            gl = g[rank * m:(rank + 1) * m].cuda().requires_grad_(True)
-            t.grad = None
-            if use_peer:
-                loss, _ = peer.peer_dense_loss(fl, gl, t, route="symmetric")
-            else:
-                loss, _ = parallel.gathered_dense_loss(fl, gl, t, route="symmetric")
-            (0.5 * loss).backward()
+        if kind.startswith("peer"):
+            # forward only (no backward between two forwards) must not disturb the exchange
+            with torch.no_grad():
+                l_eval = fn(fl.detach(), gl.detach(), t.detach())
+                l_eval2 = fn(fl.detach(), gl.detach(), t.detach())
             torch.cuda.synchronize()
-            out.append(tuple(x.detach().cpu() for x in (loss, fl.grad, gl.grad, t.grad)))
-        if use_peer:
-            gs = peer.PeerGraphedStep(fl.detach(), gl.detach(), t.detach(), route="symmetric")
+            assert float(l_eval) == float(l_eval2) == float(out[-1][0])
+            # graphed replay: two graphs (one per parity), several replays on the last data, bit-identical to eager
+            route = "symmetric" if kind == "peer-symmetric" else "reduce"
+            part = kind.split("-")[1] if route == "reduce" else None
+            gs = peer.PeerGraphedStep(fl.detach(), gl.detach(), t.detach(), route=route, partials=part)
             gs.gamma.fill_(0.5)
             for _ in range(5):
                 l2, df2, dg2, dt2 = gs()
             torch.cuda.synchronize()
             out.append(tuple(x.detach().cpu().clone() for x in (l2, df2, dg2, dt2)))
+            assert peer.PeerExchange.wait_error() is None
         results[rank] = out
     finally:
         dist.destroy_process_group()
 
 
-@_SYMMETRIC
-@pytest.mark.parametrize("use_peer", [False, True])
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_symmetric_route_matches_single_gpu(world, use_peer):
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    results = mp.Manager().dict()
-    mp.spawn(_symmetric_worker, args=(world, _free_port(), results, use_peer), nprocs=world, join=True)
-    m = B // world
-    for si, seed in enumerate((0, 1, 2)):
-        f, g = orc.synth_embeddings(B, D, seed=seed, correlated=True)
-        fd, gd = f.double(), g.double()
+def _check(results, world, b, d, graphed):
+    dev = "cuda" if b * b > 1 << 22 else "cpu"        # the fp64 oracle of the BASELINE shape runs on the GPU
+    m = b // world
+    worst = 0.0
+    for si, seed in enumerate(SEEDS):
+        f, g = orc.synth_embeddings(b, d, seed=seed, correlated=True)
+        fd, gd = f.double().to(dev), g.double().to(dev)
         df, dg, dt = orc.jsd_dense_grads(fd, gd, orc.T_INIT, gamma=0.5)
         tot_dt = 0.0
         for r in range(world):
             loss, gf, gg, gt = results[r][si]
             slab = orc.jsd_dense(fd[r * m:(r + 1) * m], gd, orc.T_INIT, row_offset=r * m)
             assert abs(float(loss) - float(slab["loss"])) < 1e-3 * float(slab["loss"])
-            ref_f, ref_g = world * df[r * m:(r + 1) * m], world * dg[r * m:(r + 1) * m]
-            assert (gf.double() - ref_f).abs().max() < 1e-2 * ref_f.abs().max()
-            assert (gg.double() - ref_g).abs().max() < 1e-2 * ref_g.abs().max()
+            ref_f, ref_g = (world * df[r * m:(r + 1) * m]).cpu(), (world * dg[r * m:(r + 1) * m]).cpu()
+            e_f = float((gf.double() - ref_f).abs().max() / ref_f.abs().max())
+            e_g = float((gg.double() - ref_g).abs().max() / ref_g.abs().max())
+            worst = max(worst, e_f, e_g)
+            assert e_f < 1e-2, (seed, r, e_f)
+            assert e_g < 1e-2, (seed, r, e_g)
             tot_dt += float(gt)
         assert abs(tot_dt / world - float(dt)) < 1e-2 * abs(float(dt))
-    if use_peer:
-        for r in range(world):
-            for a, b in zip(results[r][2], results[r][3]):
-                assert torch.equal(a, b)
+    if graphed:
+        for r in range(world):      # graph replay == eager on the same data (deterministic kernels, fixed slot order)
+            for a, bb in zip(results[r][len(SEEDS) - 1], results[r][len(SEEDS)]):
+                assert torch.equal(a, bb)
+    return worst
+
+
+KINDS = ["nccl-reduce", "nccl-symmetric", "peer-bf16", "peer-fp32", "peer-symmetric"]
+
+
+@pytest.mark.parametrize("b,d", SHAPES)
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharded_dense_matches_single_gpu(world, kind, b, d):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world == 1 and not kind.startswith("peer"):
+        pytest.skip("world 1 exercises the peer kernels only")
+    results = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), results, kind, b, d), nprocs=world, join=True)
+    worst = _check(results, world, b, d, graphed=kind.startswith("peer"))
+    print(f"world={world} {kind} B={b} D={d}: worst gradient error {worst:.2e} (tolerance 1e-2)")
+
+
+def test_logged_global_loss_is_the_mean_of_the_slab_losses():
+    world = min(torch.cuda.device_count(), 2)
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_logging_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    f, g = orc.synth_embeddings(512, 128, seed=0, correlated=True)
+    full = orc.jsd_dense(f.double(), g.double(), orc.T_INIT)
+    for r in range(world):
+        assert abs(results[r] - float(full["loss"])) < 1e-3 * float(full["loss"])
+
+
+def _logging_worker(rank, world, port, results):
+    from clip_lite_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        f, g = orc.synth_embeddings(512, 128, seed=0, correlated=True)
+        m = 512 // world
+        t = torch.tensor(orc.T_INIT, device="cuda")
+        loss, _ = parallel.gathered_dense_loss(f[rank * m:(rank + 1) * m].cuda(), g[rank * m:(rank + 1) * m].cuda(), t)
+        results[rank] = float(parallel.global_loss_for_logging(loss))
+    finally:
+        dist.destroy_process_group()

@@ -257,7 +257,7 @@ int launch_normalize_bwd(const jsd::NormBwdJob& job, int count, int64_t rows, in
 // events, so the pattern is legal inside a CUDA-graph capture of the caller's stream.  JSD_OVERLAP=0 disables it.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, mid2 = nullptr;
 };
 
 SideStream* side_stream() {
@@ -274,12 +274,57 @@ SideStream* side_stream() {
   if (s.stream == nullptr) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.mid, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.mid2, cudaEventDisableTiming) != cudaSuccess) {
       s = SideStream{};
       return nullptr;
     }
   }
   return &s;
+}
+
+// All-gather of the text rows by the COPY ENGINES: a few non-blocking streams per device on which
+// jsd_peer_normalize_push enqueues, behind the normalise launch, one peer-to-peer copy of this rank's row block per
+// destination, each followed by a 4-byte copy of the step counter into the destination's "rows of rank r are in"
+// flag (stream order = the flag lands after the rows).  No SM is involved and nothing is fenced: pushing from the
+// forward kernel's idle warps works too (JSD_PEER_GATHER=sm) but a system-scope fence per destination takes 30-40 us
+// on an SM that is busy feeding the tensor cores (traces r02d / r02f).  jsd_peer_dense_fwd joins the copy streams
+// behind its launch, so the exchange runs underneath the forward and everything later is ordered after it.
+constexpr int kCopyStreams = 3;
+struct CopyStreams {
+  cudaStream_t stream[kCopyStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kCopyStreams] = {nullptr, nullptr, nullptr};
+  bool pending = false;
+};
+
+CopyStreams* copy_streams() {
+  static CopyStreams per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  CopyStreams& c = per_dev[dev];
+  if (c.fork == nullptr) {
+    bool ok = cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kCopyStreams && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&c.stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      c = CopyStreams{};
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return &c;
+}
+
+// JSD_PEER_GATHER = ce (default: copy engines) | sm (stores from the forward kernel's idle warps)
+bool peer_gather_by_copy_engine() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JSD_PEER_GATHER");
+    v = (e && e[0] == 's') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 // Peer waits (ptx.cuh: WaitCfg): time limit + host-mapped error word, installed once per device.
@@ -412,6 +457,9 @@ struct PeerWait {
   const int* counter = nullptr;
   int count = 0;
   int rows = 0;        // rows per source rank (0: wait for every rank before the first load)
+  const jsd_peer_ctx* ctx = nullptr;   // set: own rows need no flag; with push_in_kernel the forward also copies
+  int parity = 0;                      // them to the other ranks
+  bool push_in_kernel = false;
 };
 int dense_fwd_impl(const void* U, const void* V, int64_t M, int64_t N, int64_t D, int64_t row_offset,
                    const float* t_dev, void* Gmat, int64_t ldg, float* gdiag, void* workspace, float* out4,
@@ -468,10 +516,25 @@ int dense_fwd_impl(const void* U, const void* V, int64_t M, int64_t N, int64_t D
   p.wait_counter = wait.counter;
   p.wait_count = wait.count;
   p.wait_rows = wait.rows;
+  p.wait_skip = -1;
   if (wait.flags != nullptr && wait.rows > 0) {
-    // start on this rank's own column block, then walk the ranks in the order their rows arrive (rank - 1, ...
-    // see normalize_push_kernel): n-blocks are visited downwards from the own block
+    // start on this rank's own column block, then walk the ranks upwards (rank + 1, rank + 2, ...): the order in
+    // which their rows arrive (every sender serves rank - 1, rank - 2, ... in turn)
     p.n_rot = (int)(row_offset / jsd::BLOCK_N);
+  }
+  if (wait.ctx != nullptr) {
+    const jsd_peer_ctx* c = wait.ctx;
+    p.wait_skip = c->rank;
+    p.gath_world = wait.push_in_kernel ? c->world : 0;
+    p.gath_chunks = (int)(c->rows * c->dim / 8);
+    const size_t own = (size_t)c->rank * c->rows * c->dim;
+    p.gath_src = reinterpret_cast<const uint4*>((const __nv_bfloat16*)c->v_all[wait.parity][c->rank] + own);
+    for (int k = 1; k < c->world; ++k) {
+      const int q = (c->rank - k + c->world) % c->world;
+      p.gath_dst[k] = reinterpret_cast<uint4*>((__nv_bfloat16*)c->v_all[wait.parity][q] + own);
+      p.gath_flag_dst[k] = c->flags[q] + JSD_PEER_READY_V + wait.parity * JSD_MAX_PEERS + c->rank;
+    }
+    p.gath_ticket = c->flags[c->rank] + JSD_PEER_TICKET_PUSH;
   }
   if (Gmat) {
     // epilogue TMA stores: box = 64 columns x 32 rows per warp; rows >= M / columns >= N are clipped
@@ -777,41 +840,39 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
   JSD_REQUIRE(F && G && U && inv_f && inv_g && (parity == 0 || parity == 1), "jsd_peer_normalize_push: bad argument");
   if (int rc = ensure_wait_cfg()) return rc;
   const int64_t rows = ctx->rows, D = ctx->dim;
-  jsd::PeerPushJob job{};
+  // local part only: F -> U, G -> this rank's row block of its OWN gathered V buffer, step counter of the buffer
+  // + 1.  The copies into the other ranks' buffers are made by the forward launch that follows (jsd_peer_dense_fwd:
+  // the all-gather is fused into its consumer and runs underneath it).
+  jsd::NormalizeJob job{};
   job.X[0] = F;
   job.X[1] = G;
-  job.U = (__nv_bfloat16*)U;
+  job.Xn[0] = (__nv_bfloat16*)U;
+  job.Xn[1] = (__nv_bfloat16*)ctx->v_all[parity][ctx->rank] + (size_t)ctx->rank * rows * D;
   job.inv_norm[0] = inv_f;
   job.inv_norm[1] = inv_g;
-  uintptr_t bits = reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(U);
-  for (int k = 0; k < ctx->world; ++k) {
-    // destination slot k = rank - k (mod world): a receiver q is therefore served by q, q + 1, q + 2, ... in turn,
-    // the order in which its forward walks the column blocks
-    const int q = (ctx->rank - k + ctx->world) % ctx->world;
-    job.v_dst[k] = (__nv_bfloat16*)ctx->v_all[parity][q] + (size_t)ctx->rank * rows * D;
-    job.flag_dst[k] = ctx->flags[q] + JSD_PEER_READY_V + parity * JSD_MAX_PEERS + ctx->rank;
-    bits |= reinterpret_cast<uintptr_t>(job.v_dst[k]);
-  }
-  int32_t* mine = ctx->flags[ctx->rank];
-  job.counter = mine + JSD_PEER_COUNTER_V + parity;
-  job.ticket = mine + JSD_PEER_TICKET_PUSH;
-  job.world = ctx->world;
-  const bool vec = (D % 8 == 0) && (bits & 15) == 0;
-  const dim3 grid((unsigned)((rows + 7) / 8), 2);
+  job.bump = ctx->flags[ctx->rank] + JSD_PEER_COUNTER_V + parity;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (dtype) {
-#define JSD_PUSH_CASE(code, T)                                                                        \
-    case code:                                                                                        \
-      if (vec) jsd::normalize_push_kernel<T, 8><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);        \
-      else jsd::normalize_push_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);            \
-      break;
-    JSD_PUSH_CASE(JSD_F32, float)
-    JSD_PUSH_CASE(JSD_BF16, __nv_bfloat16)
-    JSD_PUSH_CASE(JSD_F16, __half)
-#undef JSD_PUSH_CASE
-    default: return fail("unsupported dtype code %d", dtype);
+  int rc = [&]() -> int { JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(job, 2, rows, D, st))); }();
+  if (rc) return rc;
+  if (ctx->world > 1 && peer_gather_by_copy_engine()) {
+    CopyStreams* cs = copy_streams();
+    JSD_REQUIRE(cs != nullptr, "jsd_peer_normalize_push: could not create the copy streams");
+    JSD_CUDA_OK(cudaEventRecord(cs->fork, st));
+    for (int i = 0; i < kCopyStreams; ++i) JSD_CUDA_OK(cudaStreamWaitEvent(cs->stream[i], cs->fork, 0));
+    const size_t own = (size_t)ctx->rank * rows * D, bytes = (size_t)rows * D * sizeof(__nv_bfloat16);
+    const __nv_bfloat16* src = (const __nv_bfloat16*)ctx->v_all[parity][ctx->rank] + own;
+    for (int k = 1; k < ctx->world; ++k) {
+      // destination rank - k (mod world): a receiver q is served by q + 1, q + 2, ... in turn, the order in which
+      // its forward walks the column blocks
+      const int q = (ctx->rank - k + ctx->world) % ctx->world;
+      cudaStream_t c = cs->stream[(k - 1) % kCopyStreams];
+      JSD_CUDA_OK(cudaMemcpyAsync((__nv_bfloat16*)ctx->v_all[parity][q] + own, src, bytes, cudaMemcpyDeviceToDevice, c));
+      JSD_CUDA_OK(cudaMemcpyAsync(ctx->flags[q] + JSD_PEER_READY_V + parity * JSD_MAX_PEERS + ctx->rank, job.bump,
+                                  sizeof(int32_t), cudaMemcpyDeviceToDevice, c));
+    }
+    for (int i = 0; i < kCopyStreams; ++i) JSD_CUDA_OK(cudaEventRecord(cs->join[i], cs->stream[i]));
+    cs->pending = true;
   }
-  JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -820,15 +881,27 @@ int jsd_peer_dense_fwd(const void* U, const jsd_peer_ctx* ctx, int parity, const
                        jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_fwd")) return rc;
   JSD_REQUIRE(parity == 0 || parity == 1, "jsd_peer_dense_fwd: parity must be 0 or 1");
+  JSD_REQUIRE(ctx->dim % 8 == 0, "jsd_peer_dense_fwd: D must be a multiple of 8");
   if (int rc = ensure_wait_cfg()) return rc;
-  const int32_t* mine = ctx->flags[ctx->rank];
+  int32_t* mine = ctx->flags[ctx->rank];
   PeerWait w;
   w.flags = mine + JSD_PEER_READY_V + parity * JSD_MAX_PEERS;
   w.counter = mine + JSD_PEER_COUNTER_V + parity;
   w.count = ctx->world;
   w.rows = peer_wait_per_source() ? (int)ctx->rows : 0;
-  return dense_fwd_impl(U, ctx->v_all[parity][ctx->rank], ctx->rows, ctx->rows * ctx->world, ctx->dim,
-                        ctx->rows * ctx->rank, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, w, stream);
+  w.ctx = ctx;
+  w.parity = parity;
+  w.push_in_kernel = !peer_gather_by_copy_engine();
+  if (int rc = dense_fwd_impl(U, ctx->v_all[parity][ctx->rank], ctx->rows, ctx->rows * ctx->world, ctx->dim,
+                              ctx->rows * ctx->rank, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, w, stream))
+    return rc;
+  if (CopyStreams* cs = copy_streams()) {
+    if (cs->pending) {          // the copies of jsd_peer_normalize_push ran underneath the forward: join them here
+      for (int i = 0; i < kCopyStreams; ++i) JSD_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, cs->join[i], 0));
+      cs->pending = false;
+    }
+  }
+  return 0;
 }
 
 // dV partial as bf16 tiles pushed by TMA stores from the contraction's epilogue into the OWNER's slots
@@ -861,9 +934,7 @@ static int peer_dv_push(const void* Gmat, int64_t ldg, const void* U, const jsd_
   }
   p.peer_counter = mine + JSD_PEER_COUNTER_DV;
   p.peer_ticket = mine + JSD_PEER_TICKET_DV;
-  p.push_ticket = mine + JSD_PEER_TICKET_DVPUSH;
   p.push_rows = (int)M;
-  p.push_expected = (int)((M / 32) * ((D + jsd::COLS_PER_WARP - 1) / jsd::COLS_PER_WARP));
   // first m-block of rank + 1's rows (own rows last: they need no link)
   const int tile_m = jsd::BLOCK_M * cg;
   p.m_rot = (int)((((int64_t)(ctx->rank + 1) % ctx->world) * M) / tile_m);
@@ -921,27 +992,37 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
   const void* V_all = ctx->v_all[parity][ctx->rank];
   const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim, off = ctx->rows * ctx->rank;
   cudaStream_t st = (cudaStream_t)stream;
-  // 1. the text-side partial first: its "complete" flags reach the peers as early as possible
-  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, partials_bf16, stream)) return rc;
+  // Two independent contractions side by side, forked right behind the forward, then -- once BOTH have finished --
+  // the two Jacobians side by side:
+  //   caller's stream : dV contraction (+ push / publish of the partial) | text-side Jacobian
+  //   helper stream   : dU contraction (split-K when underfilled)        | image-side Jacobian
+  // Both contractions are persistent kernels with static work lists, so any number of their CTAs may be resident:
+  // whichever gets the SMs first, the other's CTA pairs move in as they retire (no ragged last wave is wasted),
+  // and the partials travel while the rest computes.  The Jacobians are held back until both contractions are
+  // done: a row kernel started next to a persistent contraction has all of its blocks made resident on the few
+  // SMs that contraction leaves free and crawls there (traces r02d / r02g: 35-48 us instead of 6).
   SideStream* side = side_stream();
-  if (side) JSD_CUDA_OK(cudaEventRecord(side->fork, st));
-  // 2. the image-side contraction (split-K when a rank's rows underfill the GPU) ...
+  cudaStream_t is = side ? side->stream : st;
+  if (side) {
+    JSD_CUDA_OK(cudaEventRecord(side->fork, st));
+    JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
+  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, partials_bf16, stream)) return rc;
   const SplitPlan su = plan_split(M, D, N, sk_workspace, 0);
-  if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0,
-                                &su))
+  if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, (jsd_stream_t)is,
+                                nullptr, 0, &su))
     return rc;
-  // 3. ... and NEXT TO it, on the helper stream, the text-side Jacobian: it waits for the peers' flags and sums
-  //    their partials (bf16: pushed into local slots while the peers' contractions ran; fp32: pulled over NVLink
-  //    now -- link-bound, it runs on the CTA pairs the contraction leaves idle and spreads out once that retires).
-  //    Enqueued after the contraction so that the latter gets its SMs first.
-  cudaStream_t ts = side ? side->stream : st;
-  if (side) JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  if (int rc = jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, partials_bf16, dG, ts))
+  if (side) {
+    JSD_CUDA_OK(cudaEventRecord(side->mid, side->stream));      // dU done
+    JSD_CUDA_OK(cudaEventRecord(side->mid2, st));               // dV done
+    JSD_CUDA_OK(cudaStreamWaitEvent(st, side->mid, 0));
+    JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->mid2, 0));
+  }
+  if (int rc = normalize_bwd_impl(F, dtype, M, D, inv_f, acc_u, &su, V_all, off, gdiag, t_dev, gamma_dev, M, dF,
+                                  rowdot, workspace, dt_out, (jsd_stream_t)is))
     return rc;
   if (side) JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
-  // 4. image-side Jacobian (+ gamma * dL_r/dt) behind the contraction
-  if (int rc = normalize_bwd_impl(F, dtype, M, D, inv_f, acc_u, &su, V_all, off, gdiag, t_dev, gamma_dev, M, dF,
-                                  rowdot, workspace, dt_out, stream))
+  if (int rc = jsd_peer_normalize_bwd_text(G, dtype, ctx, inv_g, U, gdiag, t_dev, gamma_dev, partials_bf16, dG, stream))
     return rc;
   if (side) JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
   return 0;

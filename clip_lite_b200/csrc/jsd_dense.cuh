@@ -148,12 +148,24 @@ struct GemmParams {
   int* peer_ticket;
   // GRADPUSH: the [M, N] output is cut into `peer_world` row blocks of push_rows rows; block q belongs to rank q
   // and is written there (tmPush[q]: [push_rows, N] bf16 in rank q's memory, box 64 x 32) by one TMA store per
-  // epilogue warp and tile.  push_ticket[q] counts the completed boxes of block q; the warp that completes the
-  // last one (push_expected of them) publishes *peer_counter + 1 to peer_flag_dst[q].
+  // epilogue warp and tile.  "Complete" is published to every rank by the last CTA, as for the fp32 partial: the
+  // consumer (the owner's text-side Jacobian) runs a whole contraction later, early per-owner flags buy nothing
+  // and a system-scope fence per box costs the epilogue 15 us per launch (trace r02b).
   int push_rows;
-  int push_expected;
-  int* push_ticket;
   alignas(64) CUtensorMap tmPush[MAX_PEERS];
+  // FWD, all-gather fused into the CONSUMER: the spare control warp of every CTA copies its share of this rank's
+  // own bf16 text rows (gath_src, written by the normalise launch just before) into the gathered-V buffer of the
+  // other ranks -- destination slot k = rank - k (mod world), one destination after the other, each with its own
+  // "rows of rank r are in" flag once every CTA is done with it -- while the other warps already score the own
+  // column block.  The exchange runs underneath the forward instead of in front of it, and no rank ever waits
+  // before it has pushed (no cross-rank cycle).
+  int gath_world;                        // 0 / 1: nothing to push
+  int gath_chunks;                       // 16-byte pieces of the own block (rows * D / 8)
+  const uint4* gath_src;
+  uint4* gath_dst[MAX_PEERS];            // slot k (k >= 1)
+  int* gath_flag_dst[MAX_PEERS];
+  int* gath_ticket;                      // [MAX_PEERS], zero between launches
+  int wait_skip;                         // source rank whose rows need no flag (this rank itself), -1: none
 };
 
 // Score of a masked (out-of-range) pair: tau * kMaskedScore is finite and so negative that
@@ -308,6 +320,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k = (p.K + CHUNK_K - 1) / CHUNK_K;
   constexpr bool IS_GRAD = is_grad_mode(MODE);
+  // a forward fed by peer GPUs may legitimately stall for as long as the peer-wait limit allows
+  const uint64_t spin_limit =
+      (MODE == MODE_FWD && p.wait_flags != nullptr) ? g_wait_cfg.timeout_ns + kSpinLimitNs : kSpinLimitNs;
   constexpr bool PUSH = MODE == MODE_GRADPUSH;
   const bool stream_k = (MODE == MODE_GRAD) && p.stream_k != 0;
 
@@ -375,12 +390,13 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // The B operand of a peer forward is gathered by the other GPUs writing into this GPU's memory, one flag per
       // source rank ("my rows are in").  A tile waits only for the ranks whose rows it is about to load, so the walk
       // (rotated to start on this rank's own column block) consumes the peers' rows in the order they land.
-      uint32_t peers_in = 0;
+      uint32_t peers_in = (p.wait_skip >= 0) ? (1u << p.wait_skip) : 0u;   // own rows: stream-ordered, no flag
       int wait_target = 0;
       if (p.wait_flags != nullptr) {
         wait_target = *p.wait_counter;
         if (p.wait_rows <= 0) {
-          wait_flags_sys(p.wait_flags, p.wait_count, wait_target, WAIT_GATHERED_ROWS);
+          for (int q = 0; q < p.wait_count; ++q)
+            if (q != p.wait_skip) wait_flag_sys(p.wait_flags, q, wait_target, WAIT_GATHERED_ROWS);
           fence_proxy_async_all();
           peers_in = 0xFFFFFFFFu;
           if (blockIdx.x == 0) trace_event(TRACE_ID, TE_PEERS_IN);
@@ -411,7 +427,7 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         for (int kc = k0; kc < k1; ++kc) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait(empty_bar(stage), phase ^ 1u, spin_limit);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES * CG);
 #pragma unroll
           for (int ka = 0; ka < KA; ++ka) {
@@ -448,11 +464,11 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
       int tile, k0, k1;
       while (it.next(tile, k0, k1)) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, spin_limit);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kc = k0; kc < k1; ++kc) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(full_bar(stage), phase, spin_limit);
           tc_fence_after();
 #pragma unroll
           for (int ka = 0; ka < KA; ++ka) {
@@ -489,6 +505,54 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ===================================================== all-gather by peer stores (FWD of a multi-GPU step)
+    // The two idle control warps of every CTA copy this rank's own text rows to the other ranks, destination after
+    // destination.  A lane's share is loaded ONCE (it is the same data for every destination) when it fits into
+    // 16 registers-quads; sixteen 16-byte loads are in flight per lane either way (the first version, four in
+    // flight from one warp, was latency-bound at 170 GB/s: trace r02d).
+    if constexpr (MODE == MODE_FWD) {
+      if (p.gath_world > 1) {
+        constexpr int GB = 16;
+        const int e = *p.wait_counter;               // this step's count (bumped by the normalise launch before)
+        const int nl = (int)gridDim.x * 64;          // pushing lanes of the grid
+        const int l0 = ((int)blockIdx.x * 2 + (warp - 2)) * 32 + lane;
+        const bool resident = p.gath_chunks <= nl * GB;
+        uint4 a[GB];
+        auto load_batch = [&](int base) {
+#pragma unroll
+          for (int i = 0; i < GB; ++i)
+            if (base + i * nl < p.gath_chunks) a[i] = __ldg(p.gath_src + base + i * nl);
+        };
+        auto store_batch = [&](uint4* dst, int base) {
+#pragma unroll
+          for (int i = 0; i < GB; ++i)
+            if (base + i * nl < p.gath_chunks) dst[base + i * nl] = a[i];
+        };
+        if (resident) load_batch(l0);
+        for (int k = 1; k < p.gath_world; ++k) {
+          uint4* dst = p.gath_dst[k];
+          if (resident) {
+            store_batch(dst, l0);
+          } else {
+            for (int base = l0; base < p.gath_chunks; base += nl * GB) {
+              load_batch(base);
+              store_batch(dst, base);
+            }
+          }
+          __threadfence_system();                      // this lane's stores have reached the destination
+          __syncwarp();
+          if (lane == 0) {
+            if (atomicAdd(p.gath_ticket + k, 1) == 2 * (int)gridDim.x - 1) {   // every pushing warp is done with k
+              __threadfence_system();
+              p.gath_ticket[k] = 0;
+              st_release_sys(p.gath_flag_dst[k], e);
+              trace_event(TK_PUSH, k == p.gath_world - 1 ? TE_END : TE_PEERS_IN);
+            }
+          }
+        }
+      }
+    }
   } else if (warp >= NUM_CTRL_WARPS) {
     // ===================================================== epilogue (each CTA drains its own 128 TMEM lanes)
     const int ew = warp - NUM_CTRL_WARPS;   // 0..7
@@ -509,22 +573,6 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       gscale = gamma * (p.t_dev ? expf(*p.t_dev) : 1.f) * p.scale;
     }
     float pos_sum = 0.f, relu_sum = 0.f, lg_sum = 0.f;   // sum softplus(-x_pos), sum max(s,0), sum log2(1+e)
-    // GRADPUSH: owner rank of the box this warp stored last (its completion is counted before the staging box is
-    // re-used).  One lane: wait until the bulk store has been WRITTEN (not merely read), make it visible system-wide,
-    // count it; whoever completes an owner's block publishes "rank r's partial for you is complete" to that owner.
-    [[maybe_unused]] int pend_owner = -1;
-    [[maybe_unused]] auto push_signal = [&](int owner) {
-      tma_store_wait_all();
-      fence_proxy_async_all();
-      __threadfence_system();
-      if (atomicAdd(p.push_ticket + owner, 1) == p.push_expected - 1) {
-        __threadfence_system();
-        const int e = *reinterpret_cast<volatile int*>(p.peer_counter) + 1;
-        p.push_ticket[owner] = 0;                  // every box of this block has been counted: re-arm
-        st_release_sys(p.peer_flag_dst[owner], e);
-      }
-    };
-
     int acc = 0;
     uint32_t acc_phase = 0;
     SegmentIter it(stream_k, worker, n_workers, num_tiles, num_k, num_n_blocks, MODE == MODE_GRAD ? p.ksplit : 1);
@@ -566,9 +614,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #define JSD_GRAD_EPI_SLEEP_NS 1000
 #endif
       if constexpr (IS_GRAD && JSD_GRAD_EPI_SLEEP_NS > 0) {
-        mbar_wait_relaxed(tfull_bar(acc), acc_phase, JSD_GRAD_EPI_SLEEP_NS);   // long wait: poll gently
+        mbar_wait_relaxed(tfull_bar(acc), acc_phase, JSD_GRAD_EPI_SLEEP_NS, spin_limit);   // long wait: poll gently
       } else {
-        mbar_wait(tfull_bar(acc), acc_phase);   // short waits: all lanes poll (4 % faster than one lane + __syncwarp)
+        mbar_wait(tfull_bar(acc), acc_phase, spin_limit);   // short waits: all lanes poll (4 % faster than one lane + __syncwarp)
       }
       tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BLOCK_N + cgrp * COLS_PER_WARP + ((uint32_t)(32 * q) << 16);
@@ -782,9 +830,8 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
         }
       }
-      if constexpr (PUSH) {            // the previous tile's box has landed in its owner's memory: count it
-        if (pend_owner >= 0 && lane == 0) push_signal(pend_owner);
-        pend_owner = -1;
+      if constexpr (PUSH) {            // the previous tile's TMA store must have read the staging box
+        if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
       uint32_t ra[CW], rb[CW];
@@ -829,7 +876,6 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_store_2d(&p.tmPush[owner], g_stage, box_col, box_row - owner * p.push_rows);
             tma_store_commit();
           }
-          pend_owner = owner;
         }
       }
       if constexpr (MODE == MODE_SCORE) {
@@ -855,11 +901,13 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         acc_phase ^= 1u;
       }
     }
-    if constexpr (MODE == MODE_GRAD) {
-      if (p.peer_world > 0) __threadfence_system();   // this thread's stores, before the CTA takes its ticket
-    }
     if constexpr (PUSH) {
-      if (pend_owner >= 0 && lane == 0) push_signal(pend_owner);
+      // every box of this warp has been WRITTEN to its owner's memory (not merely read from the staging box)
+      // before the CTA takes its ticket below
+      if (lane == 0) {
+        tma_store_wait_all();
+        fence_proxy_async_all();
+      }
     }
     if constexpr (MODE == MODE_FWD) {
       if (p.gmat != nullptr && lane == 0) tma_store_wait_all();   // smem must outlive the last store
@@ -894,6 +942,8 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // out together instead of one after the other.  GRADPUSH: the flags went out per owner block already; the
     // last CTA only advances the launch counter they were derived from.
     if (p.peer_world > 0) {
+      // (the barrier above orders every thread's stores before thread 0's fence, which is cumulative: one
+      //  system-scope fence per CTA instead of one per epilogue thread)
       volatile int* s_last = reinterpret_cast<volatile int*>(smem_raw);
       if (threadIdx.x == 0) {
         __threadfence_system();
@@ -909,11 +959,9 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           *p.peer_ticket = 0;
         }
         __syncthreads();
-        if constexpr (!PUSH) {
-          if ((int)threadIdx.x < p.peer_world) {
-            __threadfence_system();
-            st_release_sys(p.peer_flag_dst[threadIdx.x], s_last[1]);
-          }
+        if ((int)threadIdx.x < p.peer_world) {
+          __threadfence_system();
+          st_release_sys(p.peer_flag_dst[threadIdx.x], s_last[1]);
         }
       }
     }

@@ -318,6 +318,8 @@ struct NormalizeJob {
   const void* X[2];
   __nv_bfloat16* Xn[2];
   float* inv_norm[2];
+  int* bump;          // optional: *bump += 1 by one thread (the peer exchange's per-buffer step counter: the forward
+                      // launch behind this one publishes / waits for exactly this value)
 };
 
 template <typename T, int VEC>
@@ -329,6 +331,7 @@ normalize_cast_kernel(const NormalizeJob job, int rows, int D) {
   float* __restrict__ inv_norm = second ? job.inv_norm[1] : job.inv_norm[0];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  if (job.bump != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *job.bump += 1;
   if (row >= rows) return;
   const T* x = X + (size_t)row * D;
   float ss = 0.f;
@@ -353,134 +356,6 @@ normalize_cast_kernel(const NormalizeJob job, int rows, int D) {
     }
   });
   if (lane == 0) inv_norm[row] = inv;
-}
-
-// ------------------------------------------------------------------ normalise + cast + all-gather by peer stores
-// Multi-GPU forward pre-pass in ONE launch: blockIdx.y = 0 normalises the image rows into the local U;
-// blockIdx.y = 1 normalises the text rows and writes each bf16 unit row into EVERY rank's gathered V buffer
-// (plain 16-byte stores to peer memory over NVLink: the all-gather is fused into the producer, there is no
-// separate collective and no second pass over the data).
-//
-// The destinations are served one after the other, starting with this rank itself and then rank + 1, rank + 2, ...
-// (mod world), and every destination gets its own "rows of rank r are in" flag as soon as ALL blocks have finished
-// with it (one ticket per destination).  At any moment every link of the switch carries one sender's rows to one
-// receiver, and the receivers' forward kernels -- which wait per source rank -- consume the blocks in the order
-// they land instead of waiting for the whole exchange (trace r02a: the all-at-once version kept the forward
-// waiting for 42-50 us per step at 8 GPUs, 14 us of which were eight release-stores issued back to back).
-struct PeerPushJob {
-  const void* X[2];              // F rows, G rows [rows, D]
-  __nv_bfloat16* U;              // local image unit rows
-  float* inv_norm[2];
-  __nv_bfloat16* v_dst[8];       // slot k: gathered V buffer of rank (rank + k) % world, offset to this rank's rows
-  int* flag_dst[8];              // slot k: that rank's flag word for this rank
-  int* counter;                  // local: pushes so far into this buffer
-  int* ticket;                   // local [8], zero between launches: blocks done with destination slot k
-  int world;
-};
-
-// 8 consecutive elements of a row as fp32
-template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&x)[8]);
-template <>
-__device__ __forceinline__ void load8<float>(const float* p, float (&x)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-}
-template <>
-__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[8]) {
-  const uint4 w = *reinterpret_cast<const uint4*>(p);
-  const uint32_t r[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    x[2 * i] = __uint_as_float(r[i] << 16);
-    x[2 * i + 1] = __uint_as_float(r[i] & 0xFFFF0000u);
-  }
-}
-template <>
-__device__ __forceinline__ void load8<__half>(const __half* p, float (&x)[8]) {
-  const uint4 w = *reinterpret_cast<const uint4*>(p);
-  const uint32_t r[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[i]));
-    x[2 * i] = f.x;
-    x[2 * i + 1] = f.y;
-  }
-}
-
-// VEC = 8: D % 8 == 0 and 16-byte aligned rows (the product's shapes); VEC = 1: anything else.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256)
-normalize_push_kernel(const __grid_constant__ PeerPushJob job, int rows, int D) {
-  const int jy = blockIdx.y;
-  if (blockIdx.x == 0 && jy == 0 && threadIdx.x == 0) trace_event(TK_PUSH, TE_START);
-  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const bool live = row < rows;
-  const T* x = X + (size_t)(live ? row : 0) * D;
-  float inv = 0.f;
-  if (live) {
-    float ss = 0.f;
-    if constexpr (VEC == 8) {
-#pragma unroll 2
-      for (int d = lane * 8; d < D; d += 256) {
-        float v[8];
-        load8<T>(x + d, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
-      }
-    } else {
-      for (int d = lane; d < D; d += 32) {
-        const float f = to_f32(x[d]);
-        ss = fmaf(f, f, ss);
-      }
-    }
-    ss = warp_sum(ss);
-    inv = 1.f / fmaxf(sqrtf(ss), kNormEps);
-    if (lane == 0) job.inv_norm[jy][row] = inv;
-  }
-  // one unit row -> one destination buffer (the row is re-read from L1: 2 KB per warp)
-  auto store_row = [&](__nv_bfloat16* dst_base) {
-    __nv_bfloat16* o = dst_base + (size_t)row * D;
-    if constexpr (VEC == 8) {
-#pragma unroll 2
-      for (int d = lane * 8; d < D; d += 256) {
-        float v[8];
-        load8<T>(x + d, v);
-        uint4 w;
-        w.x = pack_bf16x2(v[0] * inv, v[1] * inv);
-        w.y = pack_bf16x2(v[2] * inv, v[3] * inv);
-        w.z = pack_bf16x2(v[4] * inv, v[5] * inv);
-        w.w = pack_bf16x2(v[6] * inv, v[7] * inv);
-        *reinterpret_cast<uint4*>(o + d) = w;
-      }
-    } else {
-      for (int d = lane; d < D; d += 32) o[d] = __float2bfloat16_rn(to_f32(x[d]) * inv);
-    }
-  };
-  if (jy == 0) {                 // image rows: local only, the forward behind this launch is stream-ordered
-    if (live) store_row(job.U);
-    return;
-  }
-  __shared__ int s_e;
-  if (threadIdx.x == 0) s_e = *reinterpret_cast<volatile int*>(job.counter) + 1;   // bumped by the very last block
-  for (int k = 0; k < job.world; ++k) {
-    if (live) store_row(job.v_dst[k]);
-    __threadfence_system();                          // this thread's stores have reached rank (rank + k) % world
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (atomicAdd(job.ticket + k, 1) == (int)gridDim.x - 1) {     // every block is done with this destination
-        __threadfence_system();
-        job.ticket[k] = 0;
-        if (k == job.world - 1) {
-          *job.counter = s_e;
-          trace_event(TK_PUSH, TE_END);
-        }
-        st_release_sys(job.flag_dst[k], s_e);
-      }
-    }
-  }
 }
 
 // Fixed-order fp64 sum of n floats by one block (deterministic); every thread of the block must call it.
@@ -665,6 +540,7 @@ normalize_cast_reg_kernel(const NormalizeJob job, int rows, int nch) {
   float* __restrict__ inv_norm = second ? job.inv_norm[1] : job.inv_norm[0];
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  if (job.bump != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *job.bump += 1;
   if (row >= rows) return;
   const int D = nch * 128;
   const T* x = X + (size_t)row * D + lane * 4;

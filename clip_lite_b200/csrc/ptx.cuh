@@ -56,21 +56,25 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 }
 // Spin on the barrier.  A pipeline bug would otherwise hang the GPU forever: after
 // ~20 s without progress the kernel traps, which surfaces as a launch failure.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+constexpr uint64_t kSpinLimitNs = 20000000000ull;
+// (`limit_ns`: kernels whose producer may legitimately wait for a PEER GPU pass the peer-wait limit + this one, so
+//  that their inner pipeline waits do not fire before the peer wait has reported what it was waiting for)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint64_t limit_ns = kSpinLimitNs) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0xFFFu) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000ull) __trap();
+      else if (now - t0 > limit_ns) __trap();
     }
   }
 }
 
 // Same, for long waits (an epilogue warp waiting ~100 us for a 128-chunk accumulator): sleep between polls.
 // The chip runs at its power cap under these kernels, so 16 warps spinning at full rate cost clock.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns,
+                                                  uint64_t limit_ns = kSpinLimitNs) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -78,7 +82,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
     if ((++spins & 0xFFu) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000ull) __trap();
+      else if (now - t0 > limit_ns) __trap();
     }
   }
 }

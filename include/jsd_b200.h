@@ -161,12 +161,15 @@ int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N
  * One process per GPU; the two exchange steps of the sharded path (all-gather of the text rows, sum of
  * the dV partials on the owner rank) are fused into the kernels that produce / consume the data, over NVLink peer
  * memory, instead of separate NCCL collectives:
- *   jsd_peer_normalize_push      normalises F -> local U, G -> V rows stored into EVERY rank's gathered V buffer,
- *                                one destination after the other (itself, rank - 1, rank - 2, ...), each with its
- *                                own "rows of rank r are in" flag as soon as all of its rows have landed
- *   jsd_peer_dense_fwd           jsd_dense_fwd on (U, this rank's gathered V); the walk starts on the rank's own
- *                                column block and every tile waits only for the flags of the ranks whose rows it
- *                                loads, so the blocks are consumed in the order they arrive (rank, rank + 1, ...)
+ *   jsd_peer_normalize_push      the local half: normalises F -> U, G -> this rank's row block of its OWN gathered V
+ *                                buffer, and advances the buffer's step counter
+ *   jsd_peer_dense_fwd           jsd_dense_fwd on (U, this rank's gathered V) with the all-gather fused into it:
+ *                                a spare warp of every CTA copies the rank's own rows into the other ranks'
+ *                                buffers (rank - 1, rank - 2, ... in turn, one "rows of rank r are in" flag per
+ *                                destination) while the other warps already score the own column block; every
+ *                                tile waits only for the flags of the ranks whose rows it loads, and the walk goes
+ *                                rank, rank + 1, ... -- the order in which the blocks arrive.  Must directly follow
+ *                                jsd_peer_normalize_push of the same parity on the same stream.
  *   jsd_peer_dense_bwd_dv        dV partial over all text rows.  partials_bf16 = 1: the contraction's epilogue
  *                                pushes every output tile as bf16 by TMA store into its OWNER's slot buffer (owner
  *                                blocks walked from rank + 1 on, one flag per owner) -- the reduce-scatter's traffic
@@ -191,8 +194,7 @@ int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N
 #define JSD_PEER_COUNTER_V 24     /* [parity] this rank's own push counter */
 #define JSD_PEER_COUNTER_DV 26
 #define JSD_PEER_TICKET_DV 28     /* CTAs of the dV launch that have finished */
-#define JSD_PEER_TICKET_PUSH 32   /* [destination slot]: blocks of the push kernel done with that destination */
-#define JSD_PEER_TICKET_DVPUSH 40 /* [owner rank]: output boxes of the dV launch landed at that owner */
+#define JSD_PEER_TICKET_PUSH 32   /* [destination slot]: CTAs of the forward launch done pushing to that destination */
 #define JSD_PEER_FLAG_INTS 64
 
 typedef struct jsd_peer_ctx {
@@ -228,10 +230,10 @@ int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ct
                                 const void* U_bf16, const float* gdiag, const float* t_dev, const float* gamma_dev,
                                 int partials_bf16, void* dG, jsd_stream_t stream);
 
-/* Whole backward of a peer-exchange step in one call: the dV partial first (its flags go out early), then the dU
- * contraction (split-K when the rank's rows underfill the GPU) with -- on a library-owned helper stream NEXT TO
- * it -- the text-side Jacobian that waits for the peers and sums their partials, then the image-side
- * Jacobian (+ dt_out = gamma * dL_r/dt).  acc_u fp32 [rows, D] and rowdot fp32 [rows] are scratch; workspace =
+/* Whole backward of a peer-exchange step in one call, as two chains forked behind the forward: on the caller's
+ * stream the dV partial (its flags go out as early as possible) and then the text-side Jacobian that waits for the
+ * peers and sums their partials; on a library-owned helper stream the dU contraction (split-K when the rank's rows
+ * underfill the GPU) and the image-side Jacobian (+ dt_out = gamma * dL_r/dt).  Joined before returning.  acc_u fp32 [rows, D] and rowdot fp32 [rows] are scratch; workspace =
  * the forward's; sk_workspace = jsd_streamk_workspace_bytes() bytes (split-K slices). */
 int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_peer_ctx* ctx, int parity,
                             const void* U_bf16, const float* inv_f, const float* inv_g, const void* Gmat_bf16,

@@ -4,7 +4,7 @@ N=${1:-2}
 TAG=${2:-r2}
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-timeout 900 python -m pytest tests/test_gpu_parallel.py -m gpu -x -q --timeout 600 -p no:cacheprovider -s -k "test_sharded_dense_matches_single_gpu and ${N}-" > gpurun_out/${TAG}_pytest_par_n$N.log 2>&1; echo "pytest exit $?"; grep -E "passed|failed|rror|worst gradient" gpurun_out/${TAG}_pytest_par_n$N.log | tail -14
+timeout 900 python -m pytest tests/test_gpu_parallel.py -m gpu -x -q --timeout 600 -p no:cacheprovider -s -k "test_sharded_dense_matches_single_gpu and (${N}- or 1-)" > gpurun_out/${TAG}_pytest_par_n$N.log 2>&1; echo "pytest exit $?"; grep -E "passed|failed|rror|worst gradient" gpurun_out/${TAG}_pytest_par_n$N.log | tail -14
 run_bench() {  # name, env...
   name=$1; shift
   env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 100 --no-cpu-baseline 2>gpurun_out/${TAG}_bench_n${N}_$name.err | grep '^{' > gpurun_out/${TAG}_bench_n${N}_$name.json

@@ -317,14 +317,24 @@ CopyStreams* copy_streams() {
   return &c;
 }
 
-// JSD_PEER_GATHER = ce (default: copy engines) | sm (stores from the forward kernel's idle warps)
-bool peer_gather_by_copy_engine() {
-  static int v = -1;
-  if (v < 0) {
+// How the text rows reach the other ranks (measured at B = 8192, D = 1024; traces under profiles/):
+//   GATHER_FWD     stores from an idle warp of the FORWARD kernel, one flag per destination: costs no SM time and
+//                  no launch, but ~10 us per destination -- hidden completely behind the forward of 2 / 4 GPUs
+//                  (E(2) = 0.985), far too slow for the 22 us forward of 8 GPUs (86-110 us);
+//   GATHER_KERNEL  the normalise launch stores every row into every rank's buffer and publishes all flags at its
+//                  end: ~25-30 us in front of the forward, independent of what the forward does;
+//   GATHER_CE      peer-to-peer copies on the copy engines underneath the forward: no SM involved, but ~10 us of
+//                  latency per copy node (70-85 us for 7 x 2 MB at 8 GPUs).
+// Default: FWD up to 4 ranks, KERNEL above; JSD_PEER_GATHER=fwd|kernel|ce overrides (A/B timing).
+enum GatherMode { GATHER_FWD = 0, GATHER_KERNEL = 1, GATHER_CE = 2 };
+int peer_gather_mode(int world) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("JSD_PEER_GATHER");
-    v = (e && e[0] == 's') ? 0 : 1;
+    forced = !e ? -1 : (e[0] == 'f' ? GATHER_FWD : (e[0] == 'k' ? GATHER_KERNEL : (e[0] == 'c' ? GATHER_CE : -1)));
   }
-  return v != 0;
+  if (forced >= 0) return forced;
+  return world <= 4 ? GATHER_FWD : GATHER_KERNEL;
 }
 
 // Peer waits (ptx.cuh: WaitCfg): time limit + host-mapped error word, installed once per device.
@@ -840,9 +850,46 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
   JSD_REQUIRE(F && G && U && inv_f && inv_g && (parity == 0 || parity == 1), "jsd_peer_normalize_push: bad argument");
   if (int rc = ensure_wait_cfg()) return rc;
   const int64_t rows = ctx->rows, D = ctx->dim;
+  const int mode = peer_gather_mode(ctx->world);
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* mine = ctx->flags[ctx->rank];
+  if (mode == GATHER_KERNEL && ctx->world > 1) {
+    jsd::PeerPushJob job{};
+    job.X[0] = F;
+    job.X[1] = G;
+    job.U = (__nv_bfloat16*)U;
+    job.inv_norm[0] = inv_f;
+    job.inv_norm[1] = inv_g;
+    uintptr_t bits = reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(U);
+    for (int k = 0; k < ctx->world; ++k) {
+      const int q = (ctx->rank - k + ctx->world) % ctx->world;
+      job.v_dst[k] = (__nv_bfloat16*)ctx->v_all[parity][q] + (size_t)ctx->rank * rows * D;
+      job.flag_dst[k] = ctx->flags[q] + JSD_PEER_READY_V + parity * JSD_MAX_PEERS + ctx->rank;
+      bits |= reinterpret_cast<uintptr_t>(job.v_dst[k]);
+    }
+    job.counter = mine + JSD_PEER_COUNTER_V + parity;
+    job.ticket = mine + JSD_PEER_TICKET_PUSH;
+    job.world = ctx->world;
+    const bool vec = (D % 8 == 0) && (bits & 15) == 0;
+    const dim3 grid((unsigned)((rows + 7) / 8), 2);
+    switch (dtype) {
+#define JSD_PUSH_CASE(code, T)                                                                        \
+      case code:                                                                                      \
+        if (vec) jsd::normalize_push_kernel<T, 8><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);      \
+        else jsd::normalize_push_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);          \
+        break;
+      JSD_PUSH_CASE(JSD_F32, float)
+      JSD_PUSH_CASE(JSD_BF16, __nv_bfloat16)
+      JSD_PUSH_CASE(JSD_F16, __half)
+#undef JSD_PUSH_CASE
+      default: return fail("unsupported dtype code %d", dtype);
+    }
+    JSD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   // local part only: F -> U, G -> this rank's row block of its OWN gathered V buffer, step counter of the buffer
-  // + 1.  The copies into the other ranks' buffers are made by the forward launch that follows (jsd_peer_dense_fwd:
-  // the all-gather is fused into its consumer and runs underneath it).
+  // + 1.  The copies into the other ranks' buffers are made underneath the forward launch that follows
+  // (jsd_peer_dense_fwd): by one of its idle warps, or by the copy engines.
   jsd::NormalizeJob job{};
   job.X[0] = F;
   job.X[1] = G;
@@ -850,11 +897,10 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
   job.Xn[1] = (__nv_bfloat16*)ctx->v_all[parity][ctx->rank] + (size_t)ctx->rank * rows * D;
   job.inv_norm[0] = inv_f;
   job.inv_norm[1] = inv_g;
-  job.bump = ctx->flags[ctx->rank] + JSD_PEER_COUNTER_V + parity;
-  cudaStream_t st = (cudaStream_t)stream;
+  job.bump = mine + JSD_PEER_COUNTER_V + parity;
   int rc = [&]() -> int { JSD_DISPATCH_DTYPE(dtype, (launch_normalize<T>(job, 2, rows, D, st))); }();
   if (rc) return rc;
-  if (ctx->world > 1 && peer_gather_by_copy_engine()) {
+  if (ctx->world > 1 && mode == GATHER_CE) {
     CopyStreams* cs = copy_streams();
     JSD_REQUIRE(cs != nullptr, "jsd_peer_normalize_push: could not create the copy streams");
     JSD_CUDA_OK(cudaEventRecord(cs->fork, st));
@@ -891,7 +937,7 @@ int jsd_peer_dense_fwd(const void* U, const jsd_peer_ctx* ctx, int parity, const
   w.rows = peer_wait_per_source() ? (int)ctx->rows : 0;
   w.ctx = ctx;
   w.parity = parity;
-  w.push_in_kernel = !peer_gather_by_copy_engine();
+  w.push_in_kernel = peer_gather_mode(ctx->world) == GATHER_FWD;
   if (int rc = dense_fwd_impl(U, ctx->v_all[parity][ctx->rank], ctx->rows, ctx->rows * ctx->world, ctx->dim,
                               ctx->rows * ctx->rank, t_dev, Gmat, ldg, gdiag, workspace, out4, loss_out, w, stream))
     return rc;

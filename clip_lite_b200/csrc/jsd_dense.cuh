@@ -505,45 +505,32 @@ jsd_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == 3) {
     // ===================================================== all-gather by peer stores (FWD of a multi-GPU step)
-    // The two idle control warps of every CTA copy this rank's own text rows to the other ranks, destination after
-    // destination.  A lane's share is loaded ONCE (it is the same data for every destination) when it fits into
-    // 16 registers-quads; sixteen 16-byte loads are in flight per lane either way (the first version, four in
-    // flight from one warp, was latency-bound at 170 GB/s: trace r02d).
+    // The spare control warp of every CTA copies its share of this rank's own text rows to the other ranks,
+    // destination after destination, each with its own flag.  Slow per destination (a system-scope fence on an SM
+    // that is busy feeding the tensor cores takes 10-30 us: traces r02d / r02f) but free -- no SM time, no launch --
+    // so the host side selects it when the forward is long enough to hide it (2 / 4 GPUs at B = 8192).
     if constexpr (MODE == MODE_FWD) {
       if (p.gath_world > 1) {
-        constexpr int GB = 16;
         const int e = *p.wait_counter;               // this step's count (bumped by the normalise launch before)
-        const int nl = (int)gridDim.x * 64;          // pushing lanes of the grid
-        const int l0 = ((int)blockIdx.x * 2 + (warp - 2)) * 32 + lane;
-        const bool resident = p.gath_chunks <= nl * GB;
-        uint4 a[GB];
-        auto load_batch = [&](int base) {
-#pragma unroll
-          for (int i = 0; i < GB; ++i)
-            if (base + i * nl < p.gath_chunks) a[i] = __ldg(p.gath_src + base + i * nl);
-        };
-        auto store_batch = [&](uint4* dst, int base) {
-#pragma unroll
-          for (int i = 0; i < GB; ++i)
-            if (base + i * nl < p.gath_chunks) dst[base + i * nl] = a[i];
-        };
-        if (resident) load_batch(l0);
+        const int first = (int)blockIdx.x * 32 + lane, stride = (int)gridDim.x * 32;
         for (int k = 1; k < p.gath_world; ++k) {
           uint4* dst = p.gath_dst[k];
-          if (resident) {
-            store_batch(dst, l0);
-          } else {
-            for (int base = l0; base < p.gath_chunks; base += nl * GB) {
-              load_batch(base);
-              store_batch(dst, base);
-            }
+          int c = first;
+          for (; c + 3 * stride < p.gath_chunks; c += 4 * stride) {      // four 16-byte pieces in flight per lane
+            const uint4 a0 = __ldg(p.gath_src + c), a1 = __ldg(p.gath_src + c + stride);
+            const uint4 a2 = __ldg(p.gath_src + c + 2 * stride), a3 = __ldg(p.gath_src + c + 3 * stride);
+            dst[c] = a0;
+            dst[c + stride] = a1;
+            dst[c + 2 * stride] = a2;
+            dst[c + 3 * stride] = a3;
           }
+          for (; c < p.gath_chunks; c += stride) dst[c] = __ldg(p.gath_src + c);
           __threadfence_system();                      // this lane's stores have reached the destination
           __syncwarp();
           if (lane == 0) {
-            if (atomicAdd(p.gath_ticket + k, 1) == 2 * (int)gridDim.x - 1) {   // every pushing warp is done with k
+            if (atomicAdd(p.gath_ticket + k, 1) == (int)gridDim.x - 1) {   // every CTA is done with destination k
               __threadfence_system();
               p.gath_ticket[k] = 0;
               st_release_sys(p.gath_flag_dst[k], e);

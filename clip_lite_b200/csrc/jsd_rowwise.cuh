@@ -358,6 +358,128 @@ normalize_cast_kernel(const NormalizeJob job, int rows, int D) {
   if (lane == 0) inv_norm[row] = inv;
 }
 
+// ------------------------------------------------------------------ normalise + cast + all-gather by peer stores
+// Multi-GPU forward pre-pass in ONE launch: blockIdx.y = 0 normalises the image rows into the local U;
+// blockIdx.y = 1 normalises the text rows and writes each bf16 unit row into EVERY rank's gathered V buffer
+// (16-byte stores to peer memory over NVLink: the all-gather is fused into the producer).  The last block bumps
+// this rank's counter and publishes it to every rank's "rows of rank r are in" flag -- one thread per destination,
+// so that the remote release-stores (a ~2 us round trip each) go out together (trace r02a: issued one after the
+// other they cost 14 us at 8 GPUs).  Selected by the host when the forward is too short to hide the in-forward
+// push (8 GPUs at B = 8192); see jsd_peer_normalize_push.
+struct PeerPushJob {
+  const void* X[2];              // F rows, G rows [rows, D]
+  __nv_bfloat16* U;              // local image unit rows
+  float* inv_norm[2];
+  __nv_bfloat16* v_dst[8];       // slot k: gathered V buffer of rank (rank - k) % world, offset to this rank's rows
+  int* flag_dst[8];              // slot k: that rank's flag word for this rank (slot 0 = this rank: unused)
+  int* counter;                  // local: pushes so far into this buffer
+  int* ticket;                   // local, zero between launches
+  int world;
+};
+
+// 8 consecutive elements of a row as fp32
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&x)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&x)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  const uint32_t r[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(r[i] << 16);
+    x[2 * i + 1] = __uint_as_float(r[i] & 0xFFFF0000u);
+  }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&x)[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  const uint32_t r[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[i]));
+    x[2 * i] = f.x;
+    x[2 * i + 1] = f.y;
+  }
+}
+
+// VEC = 8: D % 8 == 0 and 16-byte aligned rows (the product's shapes); VEC = 1: anything else.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_push_kernel(const __grid_constant__ PeerPushJob job, int rows, int D) {
+  const int jy = blockIdx.y;
+  if (blockIdx.x == 0 && jy == 0 && threadIdx.x == 0) trace_event(TK_PUSH, TE_START);
+  const T* __restrict__ X = static_cast<const T*>(job.X[jy]);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row < rows) {
+    const T* x = X + (size_t)row * D;
+    float ss = 0.f;
+    if constexpr (VEC == 8) {
+#pragma unroll 2
+      for (int d = lane * 8; d < D; d += 256) {
+        float v[8];
+        load8<T>(x + d, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const float f = to_f32(x[d]);
+        ss = fmaf(f, f, ss);
+      }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), kNormEps);
+    if (lane == 0) job.inv_norm[jy][row] = inv;
+    const int ndst = jy == 0 ? 1 : job.world;
+    if constexpr (VEC == 8) {
+      for (int d = lane * 8; d < D; d += 256) {      // the row is re-read from L1; one packed piece -> every rank
+        float v[8];
+        load8<T>(x + d, v);
+        uint4 w;
+        w.x = pack_bf16x2(v[0] * inv, v[1] * inv);
+        w.y = pack_bf16x2(v[2] * inv, v[3] * inv);
+        w.z = pack_bf16x2(v[4] * inv, v[5] * inv);
+        w.w = pack_bf16x2(v[6] * inv, v[7] * inv);
+        for (int k = 0; k < ndst; ++k)
+          *reinterpret_cast<uint4*>((jy == 0 ? job.U : job.v_dst[k]) + (size_t)row * D + d) = w;
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const __nv_bfloat16 r = __float2bfloat16_rn(to_f32(x[d]) * inv);
+        for (int k = 0; k < ndst; ++k) ((jy == 0 ? job.U : job.v_dst[k]) + (size_t)row * D)[d] = r;
+      }
+    }
+  }
+  __shared__ int s_flag[2];
+  __syncthreads();                                   // the block's stores, before thread 0's (cumulative) fence
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_flag[0] = (atomicAdd(job.ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
+  }
+  __syncthreads();
+  if (s_flag[0]) {
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const int e = *job.counter + 1;
+      *job.counter = e;
+      s_flag[1] = e;
+      *job.ticket = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 1 && (int)threadIdx.x < job.world) {      // slot 0 is this rank itself: stream-ordered
+      __threadfence_system();
+      st_release_sys(job.flag_dst[threadIdx.x], s_flag[1]);
+    }
+    if (threadIdx.x == 0) trace_event(TK_PUSH, TE_END);
+  }
+}
+
 // Fixed-order fp64 sum of n floats by one block (deterministic); every thread of the block must call it.
 __device__ __forceinline__ void block_reduce_to(const float* src, int n, float* out) {
   __shared__ double s_red[256];
@@ -592,6 +714,38 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
 #pragma unroll
     for (int i = 0; i < ROW_REG_CHUNKS; ++i)
       if (i < nch) dv[i] = __ldcs(reinterpret_cast<const float4*>(acc + aoff + i * 128));
+  } else if (job.slot_bf16) {
+    // bf16 partials pushed by the peers: FOUR slots' loads are in flight together (raw 8-byte pieces, 16 registers
+    // per slot); one slot at a time, 8 GPUs cost eight dependent round trips per row -- 18 us for 1024 rows (trace
+    // r02h).  Added in rank order either way (deterministic).
+#pragma unroll
+    for (int i = 0; i < ROW_REG_CHUNKS; ++i) dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s0 = 0; s0 < 8; s0 += 4) {
+      if (s0 < job.acc_slots) {
+        uint2 raw[4][ROW_REG_CHUNKS];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s0 + s < job.acc_slots) {
+            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(job.slot[s0 + s]) + aoff;
+#pragma unroll
+            for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+              if (i < nch) raw[s][i] = __ldcs(reinterpret_cast<const uint2*>(a + i * 128));
+          }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s0 + s < job.acc_slots) {
+#pragma unroll
+            for (int i = 0; i < ROW_REG_CHUNKS; ++i)
+              if (i < nch) {
+                dv[i].x += __uint_as_float(raw[s][i].x << 16);
+                dv[i].y += __uint_as_float(raw[s][i].x & 0xFFFF0000u);
+                dv[i].z += __uint_as_float(raw[s][i].y << 16);
+                dv[i].w += __uint_as_float(raw[s][i].y & 0xFFFF0000u);
+              }
+          }
+      }
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < ROW_REG_CHUNKS; ++i) dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU box, short: bench N=8 / N=4 (peer, bf16 partials) + kernel timeline at N=8
+# 8-GPU box, short: bench N=8 / N=4 (peer, bf16 partials, gather variants) + kernel timeline at N=8
 TAG=${1:-r2f}
 mkdir -p gpurun_out
 run_bench() {  # N name extra-args -- env...
@@ -16,7 +16,8 @@ except Exception as e:
 PY
   grep -v "^W\|^\*\*\*\|OMP_NUM\|^$" gpurun_out/${TAG}_bench_n${N}_$name.err | tail -3
 }
-run_bench 8 bf16 "" JSD_PEER_PARTIALS=bf16
-run_bench 4 bf16 "" JSD_PEER_PARTIALS=bf16
+run_bench 8 default "" JSD_PEER_PARTIALS=bf16
+run_bench 4 default "" JSD_PEER_PARTIALS=bf16
+run_bench 4 kernel "" JSD_PEER_PARTIALS=bf16 JSD_PEER_GATHER=kernel
 JSD_PEER_PARTIALS=bf16 JSD_LIB=$PWD/clip_lite_b200/csrc/libjsd_b200_trace.so timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/trace_peer.py 8192 1024 reduce > gpurun_out/${TAG}_trace_n8_bf16.log 2>&1; echo "trace exit $?"
-grep -v "^W\|^\*\*\*\|OMP_NUM" gpurun_out/${TAG}_trace_n8_bf16.log | head -48
+grep -v "^W\|^\*\*\*\|OMP_NUM" gpurun_out/${TAG}_trace_n8_bf16.log | head -40

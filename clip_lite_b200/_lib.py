@@ -22,7 +22,8 @@ SIGNATURES = {
     "jsd_sm_count": (c_int, []),
     "jsd_index_workspace_bytes": (c_size_t, [c_int64]),
     "jsd_index_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                  c_void_p]),
     "jsd_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "jsd_dense_workspace_bytes": (c_size_t, []),
     "jsd_dense_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
@@ -86,7 +87,7 @@ class PeerCtx(ctypes.Structure):
                 ("flags", c_void_p * MAX_PEERS)]
 
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 _lib = None
 
 

@@ -124,7 +124,7 @@ enum SkPolicy { SK_UNDERFILLED = 1, SK_RAGGED = 2 };
 
 template <int MODE, bool A_MN, bool B_MN, int CG>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams p, void* sk_workspace,
-                cudaStream_t st, int sk_policy = SK_RAGGED) {
+                cudaStream_t st, int sk_policy = SK_RAGGED, int worker_cap = 0) {
   auto kern = jsd::jsd_gemm_kernel<MODE, A_MN, B_MN, CG>;
   constexpr int smem = jsd::gemm_smem_bytes(CG, MODE);
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it once per device
@@ -138,7 +138,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
   }
   const int sms = sm_count_cached();
   JSD_REQUIRE(sms >= CG, "no CUDA device");
-  const int max_workers = sms / CG;                         // a worker = one CTA or one CTA pair
+  int max_workers = sms / CG;                               // a worker = one CTA or one CTA pair
+  if (worker_cap > 0 && worker_cap / CG < max_workers) max_workers = worker_cap / CG;   // worker_cap: SMs this launch
+                                                                                        // may take (a sibling launch
+                                                                                        // gets the others)
+  JSD_REQUIRE(max_workers >= 1, "worker cap too small");
   const int n_blocks = (p.N + jsd::BLOCK_N - 1) / jsd::BLOCK_N;
   const long long tiles = (long long)((p.M + jsd::BLOCK_M * CG - 1) / (jsd::BLOCK_M * CG)) * n_blocks;
   const long long work_items = tiles * (MODE == jsd::MODE_GRAD && p.ksplit > 1 ? p.ksplit : 1);   // split-K slices
@@ -186,9 +190,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, jsd::GemmParams 
 
 template <int MODE>
 int launch_gemm_any(bool a_mn, bool b_mn, int cg, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                    const jsd::GemmParams& p, void* sk_workspace, cudaStream_t st, int sk_policy = SK_RAGGED) {
-#define JSD_GEMM_CASE(A, B, C) \
-  if (a_mn == A && b_mn == B && cg == C) return launch_gemm<MODE, A, B, C>(tmA, tmB, p, sk_workspace, st, sk_policy);
+                    const jsd::GemmParams& p, void* sk_workspace, cudaStream_t st, int sk_policy = SK_RAGGED,
+                    int worker_cap = 0) {
+#define JSD_GEMM_CASE(A, B, C)           \
+  if (a_mn == A && b_mn == B && cg == C) \
+    return launch_gemm<MODE, A, B, C>(tmA, tmB, p, sk_workspace, st, sk_policy, worker_cap);
   JSD_GEMM_CASE(false, false, 1) JSD_GEMM_CASE(false, true, 1) JSD_GEMM_CASE(true, false, 1) JSD_GEMM_CASE(true, true, 1)
   JSD_GEMM_CASE(false, false, 2) JSD_GEMM_CASE(false, true, 2) JSD_GEMM_CASE(true, false, 2) JSD_GEMM_CASE(true, true, 2)
 #undef JSD_GEMM_CASE
@@ -200,17 +206,19 @@ bool fits_int(int64_t v) { return v > 0 && v < (int64_t)1 << 30; }
 template <typename T>
 int launch_index(const void* F, const void* G, int64_t B, int64_t D, const int32_t* neg, const int32_t* iptr,
                  const int32_t* iidx, const float* t_dev, float* coefp, float* partials, void* dF, void* dG,
-                 float grad_scale, cudaStream_t st) {
+                 float grad_scale, const float* gamma_dev, cudaStream_t st) {
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) |
                                      reinterpret_cast<uintptr_t>(dF) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0;
   const unsigned grid = (unsigned)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA);
   const int threads = 32 * jsd::INDEX_ROWS_PER_CTA;
   if (vec)
     jsd::jsd_index_kernel<T, 4><<<grid, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr, iidx,
-                                                          t_dev, coefp, partials, (T*)dF, (T*)dG, grad_scale);
+                                                          t_dev, coefp, partials, (T*)dF, (T*)dG, grad_scale,
+                                                          gamma_dev);
   else
     jsd::jsd_index_kernel<T, 1><<<grid, threads, 0, st>>>((const T*)F, (const T*)G, (int)B, (int)D, neg, iptr, iidx,
-                                                          t_dev, coefp, partials, (T*)dF, (T*)dG, grad_scale);
+                                                          t_dev, coefp, partials, (T*)dF, (T*)dG, grad_scale,
+                                                          gamma_dev);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -394,7 +402,7 @@ int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; 
 
 extern "C" {
 
-int jsd_abi_version(void) { return 8; }
+int jsd_abi_version(void) { return 9; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -404,7 +412,8 @@ size_t jsd_index_workspace_bytes(int64_t B) { return (size_t)(B > 0 ? B : 0) * 4
 
 int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
                       const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
-                      float* out4, float* loss_out, void* dF, void* dG, float grad_scale, jsd_stream_t stream) {
+                      float* out4, float* loss_out, void* dF, void* dG, float grad_scale, const float* gamma_dev,
+                      jsd_stream_t stream) {
   JSD_REQUIRE(F && G && t_dev && workspace && out4, "jsd_index_fwd_bwd: null pointer argument");
   JSD_REQUIRE((dF == nullptr) == (dG == nullptr), "jsd_index_fwd_bwd: dF and dG must be given together");
   JSD_REQUIRE(grad_scale > 0.f, "jsd_index_fwd_bwd: grad_scale must be positive");
@@ -416,7 +425,7 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
   float* partials = coefp + B;
   int rc = [&]() -> int {
     JSD_DISPATCH_DTYPE(dtype, (launch_index<T>(F, G, B, D, neg_index, inv_ptr, inv_idx, t_dev, coefp, partials, dF,
-                                               dG, grad_scale, st)));
+                                               dG, grad_scale, gamma_dev, st)));
   }();
   if (rc) return rc;
   jsd::finalize_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>(
@@ -562,7 +571,7 @@ size_t jsd_streamk_flag_bytes(void) { return streamk_flag_bytes(); }
 
 // split-K partial slices of an underfilled GRAD launch: (ksplit - 1) * rows * D floats with tiles * ksplit <= 74 CTA
 // pairs, i.e. at most 74 * 256 * 256 floats; two regions (dU and dV of one step may be live together)
-constexpr size_t kSplitRegionBytes = (size_t)80 * 256 * 256 * sizeof(float);
+constexpr size_t kSplitRegionBytes = (size_t)7 * 2048 * 1024 * sizeof(float);   // 7 extra slices of a 2048 x 1024 block
 
 size_t jsd_streamk_workspace_bytes(void) {
   const size_t sk = (size_t)jsd::SK_MAX_CTAS * jsd::SK_SLOT_FLOATS * sizeof(float);
@@ -620,7 +629,7 @@ static SplitPlan plan_split(int64_t rows, int64_t D, int64_t kdim, void* workspa
 static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* X, int64_t M, int64_t N, int64_t D,
                             const float* t_dev, const float* gamma_dev, void* sk_workspace, float* out,
                             jsd_stream_t stream, const jsd_peer_ctx* peer = nullptr, int sk_policy = SK_RAGGED,
-                            const SplitPlan* split = nullptr) {
+                            const SplitPlan* split = nullptr, int worker_cap = 0) {
   JSD_REQUIRE(Gmat && X && t_dev && (out || peer), "jsd_dense_bwd: null pointer argument");
   JSD_REQUIRE(fits_int(M) && fits_int(N) && fits_int(D), "jsd_dense_bwd: M=%lld N=%lld D=%lld out of range",
               (long long)M, (long long)N, (long long)D);
@@ -663,7 +672,7 @@ static int dense_bwd_common(bool dv, const void* Gmat, int64_t ldg, const void* 
     p.peer_ticket = mine + JSD_PEER_TICKET_DV;
   }
   return launch_gemm_any<jsd::MODE_GRAD>(dv, true, pick_cta_group(rows), tmA, tmB, p, sk_workspace,
-                                          (cudaStream_t)stream, sk_policy);
+                                          (cudaStream_t)stream, sk_policy, worker_cap);
 }
 
 int jsd_dense_bwd_du(const void* Gmat, int64_t ldg, const void* V, int64_t M, int64_t N, int64_t D,
@@ -853,7 +862,7 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
   const int mode = peer_gather_mode(ctx->world);
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* mine = ctx->flags[ctx->rank];
-  if (mode == GATHER_KERNEL && ctx->world > 1) {
+  if (mode == GATHER_KERNEL) {   // (also at world 1 when forced: the single-GPU tests cover the bulk-store path)
     jsd::PeerPushJob job{};
     job.X[0] = F;
     job.X[1] = G;
@@ -870,13 +879,20 @@ int jsd_peer_normalize_push(const void* F, const void* G, int dtype, const jsd_p
     job.counter = mine + JSD_PEER_COUNTER_V + parity;
     job.ticket = mine + JSD_PEER_TICKET_PUSH;
     job.world = ctx->world;
-    const bool vec = (D % 8 == 0) && (bits & 15) == 0;
+    const size_t smem = (size_t)8 * D * sizeof(__nv_bfloat16);      // one bf16 row per warp
+    const bool vec = (D % 8 == 0) && (bits & 15) == 0 && smem <= 160 * 1024;
     const dim3 grid((unsigned)((rows + 7) / 8), 2);
     switch (dtype) {
 #define JSD_PUSH_CASE(code, T)                                                                        \
       case code:                                                                                      \
-        if (vec) jsd::normalize_push_kernel<T, 8><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);      \
-        else jsd::normalize_push_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);          \
+        if (vec) {                                                                                    \
+          if (smem > 48 * 1024)                                                                       \
+            JSD_CUDA_OK(cudaFuncSetAttribute(jsd::normalize_push_kernel<T, 8>,                        \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+          jsd::normalize_push_kernel<T, 8><<<grid, 256, smem, st>>>(job, (int)rows, (int)D);          \
+        } else {                                                                                      \
+          jsd::normalize_push_kernel<T, 1><<<grid, 256, 0, st>>>(job, (int)rows, (int)D);             \
+        }                                                                                             \
         break;
       JSD_PUSH_CASE(JSD_F32, float)
       JSD_PUSH_CASE(JSD_BF16, __nv_bfloat16)
@@ -953,7 +969,7 @@ int jsd_peer_dense_fwd(const void* U, const jsd_peer_ctx* ctx, int parity, const
 // dV partial as bf16 tiles pushed by TMA stores from the contraction's epilogue into the OWNER's slots
 // (stage[q] viewed as [world][rows][D] bf16: slot = source rank), owner blocks walked from rank + 1 on
 static int peer_dv_push(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
-                        const float* gamma_dev, jsd_stream_t stream) {
+                        const float* gamma_dev, jsd_stream_t stream, int worker_cap = 0) {
   const int64_t M = ctx->rows, N = ctx->rows * ctx->world, D = ctx->dim;
   JSD_REQUIRE(Gmat && U && t_dev, "jsd_peer_dense_bwd_dv: null pointer argument");
   JSD_REQUIRE(D % 8 == 0 && ldg >= N && ldg % 8 == 0, "jsd_peer_dense_bwd_dv: bad D / ldg");
@@ -985,17 +1001,57 @@ static int peer_dv_push(const void* Gmat, int64_t ldg, const void* U, const jsd_
   const int tile_m = jsd::BLOCK_M * cg;
   p.m_rot = (int)((((int64_t)(ctx->rank + 1) % ctx->world) * M) / tile_m);
   cudaStream_t st = (cudaStream_t)stream;
-  return cg == 2 ? launch_gemm<jsd::MODE_GRADPUSH, true, true, 2>(tmA, tmB, p, nullptr, st, 0)
-                 : launch_gemm<jsd::MODE_GRADPUSH, true, true, 1>(tmA, tmB, p, nullptr, st, 0);
+  return cg == 2 ? launch_gemm<jsd::MODE_GRADPUSH, true, true, 2>(tmA, tmB, p, nullptr, st, 0, worker_cap)
+                 : launch_gemm<jsd::MODE_GRADPUSH, true, true, 1>(tmA, tmB, p, nullptr, st, 0, worker_cap);
+}
+
+static int peer_dv_impl(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
+                        const float* gamma_dev, int partials_bf16, jsd_stream_t stream, int cap_sms) {
+  if (partials_bf16) return peer_dv_push(Gmat, ldg, U, ctx, t_dev, gamma_dev, stream, cap_sms);
+  // fp32: the partial is read by the peers as one buffer: whole tiles only
+  return dense_bwd_common(true, Gmat, ldg, U, ctx->rows, ctx->rows * ctx->world, ctx->dim, t_dev, gamma_dev, nullptr,
+                          nullptr, stream, ctx, 0, nullptr, cap_sms);
 }
 
 int jsd_peer_dense_bwd_dv(const void* Gmat, int64_t ldg, const void* U, const jsd_peer_ctx* ctx, const float* t_dev,
                           const float* gamma_dev, int partials_bf16, jsd_stream_t stream) {
   if (int rc = check_peer_ctx(ctx, "jsd_peer_dense_bwd_dv")) return rc;
-  if (partials_bf16) return peer_dv_push(Gmat, ldg, U, ctx, t_dev, gamma_dev, stream);
-  // fp32: the partial is read by the peers as one buffer: whole tiles only
-  return dense_bwd_common(true, Gmat, ldg, U, ctx->rows, ctx->rows * ctx->world, ctx->dim, t_dev, gamma_dev, nullptr,
-                          nullptr, stream, ctx, 0);
+  return peer_dv_impl(Gmat, ldg, U, ctx, t_dev, gamma_dev, partials_bf16, stream, 0);
+}
+
+// Small slabs (4 / 8 GPUs at B = 8192): each backward contraction is one or two rounds of tiles, so a launch is
+// mostly fixed cost -- prologue, pipeline fill, the un-overlapped last epilogue, the drain of the pushed tiles
+// (trace r02j: 28 + 24 us for 2 x 17 GFLOP).  Run side by side on HALF of the SMs each, the two launches pay those
+// costs at the same time and each half stays busy for 3-4 rounds.  The image-side contraction is cut along K into
+// as many slices as make its units as long as a dV tile (K_dU / K_dV = world), summed in order by the Jacobian.
+struct PairedPlan {
+  int cap_sms = 0;          // 0: not paired (full-width launches, dU split by plan_split)
+  SplitPlan su;
+};
+
+static PairedPlan plan_paired(int64_t M, int64_t N, int64_t D, void* sk_workspace) {
+  PairedPlan pp;
+  static int enabled = -1;                                     // development knob: JSD_PAIRED=0 disables it
+  if (enabled < 0) {
+    const char* e = getenv("JSD_PAIRED");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int sms = sm_count_cached();
+  if (!enabled || sk_workspace == nullptr || side_stream() == nullptr || sms < 8 || M <= jsd::BLOCK_M) return pp;
+  const int64_t tiles_dv = ((N + 255) / 256) * ((D + jsd::BLOCK_N - 1) / jsd::BLOCK_N);
+  if (tiles_dv > sms || M > 2048) return pp;                   // many rounds, or long tiles (K = M): fixed costs are
+                                                               // small next to the tiles themselves, leave it
+  const int64_t nk = (N + 127) / 128;                          // k-chunks of the dU contraction (2 k-atoms each)
+  int64_t ks = N / M;                                          // = world
+  if (ks > 8) ks = 8;
+  while (ks > 1 && (nk / ks < 2 || (size_t)(ks - 1) * M * D * sizeof(float) > kSplitRegionBytes)) --ks;
+  pp.cap_sms = (sms / 4) * 2;                                  // an even number of SMs: whole CTA pairs
+  if (ks > 1) {
+    pp.su.ksplit = (int)ks;
+    pp.su.slice_base = reinterpret_cast<float*>(static_cast<char*>(sk_workspace) + streamk_flag_bytes());
+    pp.su.slice_stride = M * D;
+  }
+  return pp;
 }
 
 int jsd_peer_normalize_bwd_text(const void* G, int dtype, const jsd_peer_ctx* ctx, const float* inv_g, const void* U,
@@ -1053,10 +1109,11 @@ int jsd_peer_dense_backward(const void* F, const void* G, int dtype, const jsd_p
     JSD_CUDA_OK(cudaEventRecord(side->fork, st));
     JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
   }
-  if (int rc = jsd_peer_dense_bwd_dv(Gmat, ldg, U, ctx, t_dev, gamma_dev, partials_bf16, stream)) return rc;
-  const SplitPlan su = plan_split(M, D, N, sk_workspace, 0);
+  const PairedPlan pp = plan_paired(M, N, D, sk_workspace);
+  if (int rc = peer_dv_impl(Gmat, ldg, U, ctx, t_dev, gamma_dev, partials_bf16, stream, pp.cap_sms)) return rc;
+  const SplitPlan su = pp.cap_sms ? pp.su : plan_split(M, D, N, sk_workspace, 0);
   if (int rc = dense_bwd_common(false, Gmat, ldg, V_all, M, N, D, t_dev, gamma_dev, nullptr, acc_u, (jsd_stream_t)is,
-                                nullptr, 0, &su))
+                                nullptr, 0, &su, pp.cap_sms))
     return rc;
   if (side) {
     JSD_CUDA_OK(cudaEventRecord(side->mid, side->stream));      // dU done

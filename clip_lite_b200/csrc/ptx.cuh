@@ -202,6 +202,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy shared -> global (bulk async group): `bytes` a multiple of 16, both addresses 16-byte aligned.
+// The destination may be peer memory: the copy leaves the SM as full-size packets, no LSU involvement.
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's bulk stores have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

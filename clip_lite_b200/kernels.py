@@ -77,11 +77,11 @@ def sm_count() -> int:
 # ------------------------------------------------------------------ index mode
 def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[torch.Tensor] = None,
                   inv_ptr: Optional[torch.Tensor] = None, inv_idx: Optional[torch.Tensor] = None,
-                  want_grad: bool = True, grad_scale: Optional[float] = None):
+                  want_grad: bool = True, grad_scale: float = 1.0, gamma: Optional[torch.Tensor] = None):
     """Reference-semantics estimator, fused fwd+bwd.  Returns (out4, loss, dF, dG, grad_scale):
-    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), loss = 0-dim copy of out4[2], dF/dG = grad_scale times the
-    gradients for upstream gradient 1 (None with want_grad=False).  grad_scale defaults to B: the per-row
-    coefficients are sigma / B, which fp16 storage would flush to subnormals before a GradScaler factor applies."""
+    out4 = [pos, neg, pos+neg, dL/dt] (fp32, device), loss = 0-dim copy of out4[2], dF/dG = grad_scale * gamma
+    times the gradients (None with want_grad=False).  ``gamma`` is the upstream gradient as a device scalar
+    (default 1); it is applied in fp32 inside the kernel, so reduced-precision gradients are rounded once."""
     _req(f, "F", ndim=2)
     _req(g, "G", dtype=f.dtype, ndim=2)
     if f.shape != g.shape:
@@ -95,7 +95,8 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
             if ix.numel() != n:
                 raise ValueError(f"{name} must have {n} entries")
     tt = _scalar(t, "temperature")
-    gs = float(b) if grad_scale is None else float(grad_scale)
+    gs = float(grad_scale)
+    gg = None if gamma is None else _scalar(gamma, "gamma")
     lib = _lib.load()
     ws = torch.empty(lib.jsd_index_workspace_bytes(b) // 4, dtype=torch.float32, device=f.device)
     out4 = torch.empty(4, dtype=torch.float32, device=f.device)
@@ -104,7 +105,8 @@ def index_fwd_bwd(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: 
     dg = torch.empty_like(g) if want_grad else None
     with _on_device(f.device):
         _lib.call("jsd_index_fwd_bwd", _ptr(f), _ptr(g), _code(f), b, d, _ptr(neg_index), _ptr(inv_ptr),
-                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(loss), _ptr(df), _ptr(dg), gs, _stream())
+                  _ptr(inv_idx), _ptr(tt), _ptr(ws), _ptr(out4), _ptr(loss), _ptr(df), _ptr(dg), gs, _ptr(gg),
+                  _stream())
     return out4, loss, df, dg, gs
 
 

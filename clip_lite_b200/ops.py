@@ -69,6 +69,12 @@ def _common(f: torch.Tensor, g: torch.Tensor):
 
 
 class _JSDIndexFn(torch.autograd.Function):
+    """Two calls of the fused kernel per training step: the forward reads F, G and returns the loss (no write-back
+    pass); the backward reads them again with the upstream gradient as a device scalar and writes dF, dG in the
+    feature dtype -- 6 B D elements of HBM traffic, where "gradients in the forward + one scaling pass in the
+    backward" moves 8, and the upstream gradient (GradScaler's factor included) is applied in fp32 before the
+    single rounding, so fp16 gradients never pass through the subnormal range."""
+
     @staticmethod
     def forward(ctx, f, g, t, neg: Optional[NegativeIndex]):
         need_grad = any(ctx.needs_input_grad)
@@ -77,25 +83,22 @@ class _JSDIndexFn(torch.autograd.Function):
             if neg is not None and neg.n != fc.shape[0]:
                 raise ValueError(f"neg_index has {neg.n} entries for a batch of {fc.shape[0]}")
             ix = neg.on(fc.device) if neg is not None else (None, None, None)
-            # eval / no_grad: the kernel skips its write-back pass
-            out4, loss, df, dg, scale = K.index_fwd_bwd(fc, gc, t, *ix, want_grad=need_grad)
+            out4, loss, _, _, _ = K.index_fwd_bwd(fc, gc, t, *ix, want_grad=False)
         if need_grad:
-            ctx.save_for_backward(df, dg, out4)
-            ctx.inv_scale = 1.0 / scale
+            ctx.save_for_backward(fc, gc, t, out4)
+            ctx.ix = ix
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
         ctx.mark_non_differentiable(out4)
         return loss, out4
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
-        df, dg, out4 = ctx.saved_tensors
-        # the stored gradients carry the kernel's grad_scale; the product with the upstream gradient is formed in
-        # fp32 and rounded to the feature dtype ONCE (an fp16 product would round twice and underflow before a
-        # GradScaler factor could lift it)
-        go = grad_loss.float()
-        gs = go * ctx.inv_scale
+        fc, gc, t, out4 = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            go = grad_loss.float()
+            _, _, df, dg, _ = K.index_fwd_bwd(fc, gc, t, *ctx.ix, want_grad=True, gamma=go)
         fd, gd, td = ctx.dtypes
-        return (gs * df.float()).to(fd), (gs * dg.float()).to(gd), (go * out4[3]).to(td), None
+        return df.to(fd), dg.to(gd), (go * out4[3]).to(td), None
 
 
 class _JSDDenseFn(torch.autograd.Function):

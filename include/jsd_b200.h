@@ -54,17 +54,21 @@ int jsd_sm_count(void);
  * workspace  >= jsd_index_workspace_bytes(B) bytes
  * out4       device float[4]: {mean softplus(-s_pos), mean softplus(s_neg), their sum, dL/dt}
  * loss_out   optional (may be NULL) separate device float receiving the loss (out4[2])
- * dF, dG     [B, D] grad_scale * dL/dF, grad_scale * dL/dG for upstream gradient 1 (same dtype as F, G); both
- *            NULL = forward only (eval / no_grad: the write-back pass is skipped)
- * grad_scale host scalar > 0 folded into the stored gradients; the caller divides it out in fp32 when it applies
- *            the upstream gradient.  1 is exact for fp32 features; with fp16 features pass B (the per-row
- *            coefficients are sigma / B: unscaled they fall into fp16's subnormal range before a GradScaler
- *            factor can lift them).
+ * dF, dG     [B, D] grad_scale * gamma * dL/dF and ... dL/dG (same dtype as F, G); both NULL = forward only (eval /
+ *            no_grad, or the forward half of an autograd step: the write-back pass is skipped)
+ * grad_scale host scalar > 0 folded into the stored gradients (1 unless the caller wants to rescale later)
+ * gamma_dev  optional (may be NULL = 1) device scalar: the upstream gradient dTotal/dCROSS (GradScaler's factor
+ *            included).  It is applied in fp32 inside the kernel, so fp16 gradients are rounded ONCE and never
+ *            pass through the subnormal range (the per-row coefficients are sigma / B).  The autograd binding calls
+ *            this entry point twice per training step: forward with dF = dG = NULL (reads F, G), backward with
+ *            gamma_dev (reads F, G again, writes dF, dG): 6 B D elements of traffic instead of the 8 of "fused
+ *            call + one scaling pass over dF, dG".
  */
 size_t jsd_index_workspace_bytes(int64_t B);
 int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_t D, const int32_t* neg_index,
                       const int32_t* inv_ptr, const int32_t* inv_idx, const float* t_dev, void* workspace,
-                      float* out4, float* loss_out, void* dF, void* dG, float grad_scale, jsd_stream_t stream);
+                      float* out4, float* loss_out, void* dF, void* dG, float grad_scale, const float* gamma_dev,
+                      jsd_stream_t stream);
 
 /* ------------------------------------------------------------------ dense mode
  * All off-diagonal pairs as negatives (BASELINE.json north star); a row slab

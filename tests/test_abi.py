@@ -51,7 +51,7 @@ def test_abi_version_and_error_channel(lib):
     # argument validation happens before any CUDA call: a null pointer is refused with a message
     rc = lib.jsd_dense_fwd(None, None, 8, 8, 8, 0, None, None, 0, None, None, None, None, None)
     assert rc != 0 and b"null pointer" in lib.jsd_last_error()
-    rc = lib.jsd_index_fwd_bwd(None, None, 0, 4, 4, None, None, None, None, None, None, None, None, None, 1.0, None)
+    rc = lib.jsd_index_fwd_bwd(None, None, 0, 4, 4, None, None, None, None, None, None, None, None, None, 1.0, None, None)
     assert rc != 0
     assert lib.jsd_index_workspace_bytes(1024) == 1024 * 16
     assert lib.jsd_dense_workspace_bytes() > 0

@@ -80,8 +80,12 @@ def test_index_vs_oracle(K, dtype, b, d, mode):
         ptr, idx = _csr_inverse(neg, b)
         args = dict(neg_index=neg.int().cuda(), inv_ptr=ptr.cuda(), inv_idx=idx.cuda())
     out4, loss, df, dg, gs = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), **args)
-    df, dg = df.float() / gs, dg.float() / gs     # stored gradients carry grad_scale (= B by default)
+    df, dg = df.float() / gs, dg.float() / gs     # stored gradients carry grad_scale (1 by default)
     assert torch.equal(loss, out4[2])
+    # the upstream gradient as a device scalar and a host-side scale: 0.25 * 4 == 1, powers of two are exact
+    _, _, df2, dg2, gs2 = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), grad_scale=4.0,
+                                          gamma=torch.tensor(0.25, device="cuda"), **args)
+    assert gs2 == 4.0 and torch.equal(df2.float(), df * gs) and torch.equal(dg2.float(), dg * gs)
     # forward only (eval / no_grad): same loss, no gradient buffers
     o4, l2, n1, n2, _ = K.index_fwd_bwd(f.cuda(), g.cuda(), dev_t(), want_grad=False, **args)
     assert n1 is None and n2 is None and torch.equal(o4, out4)
@@ -131,8 +135,8 @@ def test_index_vs_reference_golden(K, golden_dir):
 
 def test_index_fp16_gradients_survive_loss_scaling():
     """fp16 features with large norms: the unscaled per-element gradient sigma / (B ||f||) is below fp16's
-    normal range; the kernel stores it times B and ops applies the upstream gradient (GradScaler's factor) in
-    fp32 before the single rounding to fp16 (ops.py:90)."""
+    normal range; the upstream gradient (GradScaler's factor) reaches the kernel as a device scalar and is applied
+    in fp32 before the single rounding to fp16 (ops.py:90)."""
     from clip_lite_b200 import ops
     b, d = 4096, 256
     f, g = orc.synth_embeddings(b, d, seed=3, correlated=True)

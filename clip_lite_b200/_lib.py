@@ -34,6 +34,16 @@ SIGNATURES = {
     "jsd_dense_backward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_dense_fused_supported": (c_int, [c_int64, c_int64]),
+    "jsd_dense_fused_splits": (c_int, [c_int64, c_int64]),
+    "jsd_dense_fused_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jsd_dense_fused_forward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "jsd_dense_fused_backward": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jsd_normalize_cast_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "jsd_dense_backward_image_side": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p,
@@ -87,7 +97,7 @@ class PeerCtx(ctypes.Structure):
                 ("flags", c_void_p * MAX_PEERS)]
 
 
-ABI_VERSION = 9
+ABI_VERSION = 11
 _lib = None
 
 

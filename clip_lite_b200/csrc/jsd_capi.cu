@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "jsd_dense.cuh"
+#include "jsd_fused.cuh"
 #include "jsd_rowwise.cuh"
 #include "jsd_score.cuh"
 
@@ -246,7 +247,8 @@ int launch_normalize_bwd(const jsd::NormBwdJob& job, int count, int64_t rows, in
   for (int i = 0; i < count; ++i)
     bits |= reinterpret_cast<uintptr_t>(job.X[i]) | reinterpret_cast<uintptr_t>(job.dX[i]) |
             reinterpret_cast<uintptr_t>(job.acc[i]) | reinterpret_cast<uintptr_t>(job.partner[i]);
-  for (int q = 0; q < job.acc_slots; ++q) bits |= reinterpret_cast<uintptr_t>(job.slot[q]);
+  for (int q = 0; q < job.acc_slots; ++q)
+    bits |= reinterpret_cast<uintptr_t>(job.slot[q]) | (count > 1 ? reinterpret_cast<uintptr_t>(job.slot1[q]) : 0);
   const bool vec = (D % 4 == 0) && (bits & 15) == 0;
   const dim3 grid((unsigned)((rows + 7) / 8), (unsigned)count);
   if (vec && D % 128 == 0 && D / 128 <= jsd::ROW_REG_CHUNKS)
@@ -402,7 +404,7 @@ int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; 
 
 extern "C" {
 
-int jsd_abi_version(void) { return 9; }
+int jsd_abi_version(void) { return 11; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -788,6 +790,124 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
   job.ticket = dt_ticket(workspace);
   job.dt_out = dt_out;
   const float inv_rows = (float)(1.0 / (double)B);
+  JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 2, B, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
+}
+
+/* ------------------------------------------------------------------ fused single-pass path (D <= 256) */
+int jsd_dense_fused_supported(int64_t B, int64_t D) {
+  return (D > 0 && D <= 256 && D % 64 == 0 && B >= 2 && (B + jsd::FB - 1) / jsd::FB * 2 <= 1024) ? 1 : 0;
+}
+
+// CTAs per 128-row block: a small batch is cut along the other modality so that the launch fills the GPU (every CTA
+// writes its own accumulator slice, summed in order by the Jacobian kernel: at most 8)
+int jsd_dense_fused_splits(int64_t B, int64_t D) {
+  (void)D;
+  if (B < 2) return 1;
+  const int64_t blocks = (B + jsd::FB - 1) / jsd::FB;
+  const int sms = sm_count_cached() > 0 ? sm_count_cached() : 148;
+  int64_t ns = sms / (2 * blocks);
+  if (ns > 8) ns = 8;
+  if (ns > blocks) ns = blocks;            // at least one 128-row tile of the other modality per CTA
+  return (int)(ns < 1 ? 1 : ns);
+}
+
+}  // extern "C"
+
+template <int NKA>
+static int launch_fused(const CUtensorMap& tmU, const CUtensorMap& tmV, const jsd::FusedParams& p, int grid,
+                        cudaStream_t st) {
+  auto kern = jsd::jsd_fused_kernel<NKA>;
+  constexpr int smem = jsd::fused_smem_bytes(NKA);
+  static unsigned long long configured_mask = 0;
+  int dev = 0;
+  JSD_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !((configured_mask >> dev) & 1ull)) {
+    JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) configured_mask |= 1ull << dev;
+  }
+  kern<<<grid, jsd::F_THREADS, smem, st>>>(tmU, tmV, p);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int jsd_dense_fused_fwd_bwd(const void* U, const void* V, int64_t B, int64_t D, const float* t_dev, float* acc_u,
+                            float* acc_v, float* gdiag, void* workspace, float* out4, float* loss_out,
+                            jsd_stream_t stream) {
+  JSD_REQUIRE(U && V && t_dev && acc_u && acc_v && gdiag && workspace && out4,
+              "jsd_dense_fused_fwd_bwd: null pointer argument");
+  JSD_REQUIRE(jsd_dense_fused_supported(B, D), "jsd_dense_fused_fwd_bwd: needs D in {64, 128, 192, 256} and "
+              "2 <= B <= 65536 (got B=%lld, D=%lld)", (long long)B, (long long)D);
+  CUtensorMap tmU, tmV;
+  if (int rc = make_tmap(&tmU, U, D, B, D, jsd::BLOCK_K, jsd::FB)) return rc;
+  if (int rc = make_tmap(&tmV, V, D, B, D, jsd::BLOCK_K, jsd::FB)) return rc;
+  jsd::FusedParams p{};
+  p.D = (int)D;
+  p.t_dev = t_dev;
+  const int blocks = (int)((B + jsd::FB - 1) / jsd::FB);
+  const int ns = jsd_dense_fused_splits(B, D);
+  p.prob[0] = jsd::FusedProblem{(int)B, (int)B, 0, acc_u, gdiag, 1};     // image rows x all text rows
+  p.prob[1] = jsd::FusedProblem{(int)B, (int)B, 0, acc_v, nullptr, 0};   // text rows x all image rows (recomputed)
+  p.blocks0 = blocks * ns;
+  p.nsplit = ns;
+  p.acc_stride = B * D;
+  p.ticket = (int*)workspace;
+  p.partials = (float*)((char*)workspace + 16);
+  p.out4 = out4;
+  p.loss_out = loss_out;
+  p.inv_pos = 1.0 / (double)B;
+  p.inv_neg = 1.0 / ((double)B * (double)(B - 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D / 64) {
+    case 1: return launch_fused<1>(tmU, tmV, p, 2 * blocks * ns, st);
+    case 2: return launch_fused<2>(tmU, tmV, p, 2 * blocks * ns, st);
+    case 3: return launch_fused<3>(tmU, tmV, p, 2 * blocks * ns, st);
+    default: return launch_fused<4>(tmU, tmV, p, 2 * blocks * ns, st);
+  }
+}
+
+int jsd_dense_fused_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev, void* U,
+                            void* V, float* inv_f, float* inv_g, float* acc_u, float* acc_v, float* gdiag,
+                            void* workspace, float* out4, float* loss_out, jsd_stream_t stream) {
+  if (int rc = jsd_normalize_cast_pair(F, G, dtype, B, D, U, V, inv_f, inv_g, stream)) return rc;
+  return jsd_dense_fused_fwd_bwd(U, V, B, D, t_dev, acc_u, acc_v, gdiag, workspace, out4, loss_out, stream);
+}
+
+int jsd_dense_fused_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U,
+                             const void* V, const float* inv_f, const float* inv_g, const float* gdiag,
+                             const float* t_dev, const float* gamma_dev, const float* acc_u, const float* acc_v,
+                             float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream) {
+  JSD_REQUIRE(F && G && U && V && inv_f && inv_g && gdiag && t_dev && acc_u && acc_v && rowdot && workspace && dF &&
+              dG && dt_out, "jsd_dense_fused_backward: null pointer argument");
+  JSD_REQUIRE(fits_int(B) && fits_int(D) && B >= 2, "jsd_dense_fused_backward: bad shape");
+  // both Jacobians (image side = job 0, text side = job 1) and gamma * dL/dt = sum_i <u_i, dU_i> in ONE launch; the
+  // accumulators are the fused kernel's unscaled sums: gamma * tau / (B (B - 1)) is applied here, in fp32
+  jsd::NormBwdJob job{};
+  job.X[0] = F;
+  job.X[1] = G;
+  job.inv_norm[0] = inv_f;
+  job.inv_norm[1] = inv_g;
+  job.acc[0] = acc_u;
+  job.acc[1] = acc_v;
+  job.partner[0] = (const __nv_bfloat16*)V;
+  job.partner[1] = (const __nv_bfloat16*)U;
+  job.dX[0] = dF;
+  job.dX[1] = dG;
+  job.rowdot = rowdot;
+  job.ticket = dt_ticket(workspace);
+  job.dt_out = dt_out;
+  job.acc_scale[0] = job.acc_scale[1] = (float)(1.0 / ((double)B * (double)(B - 1)));
+  const int ns = jsd_dense_fused_splits(B, D);
+  if (ns > 1) {                           // the accumulators are sums of the column splits' slices, in order
+    job.acc_slots = ns;
+    for (int q = 0; q < ns; ++q) {
+      job.slot[q] = acc_u + (size_t)q * B * D;
+      job.slot1[q] = acc_v + (size_t)q * B * D;
+    }
+  }
+  const float inv_rows = (float)(1.0 / (double)B);
+  cudaStream_t st = (cudaStream_t)stream;
   JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 2, B, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
 }
 

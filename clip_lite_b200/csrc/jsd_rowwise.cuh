@@ -72,9 +72,14 @@ template <>
 __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
 // Visit a row 4 elements at a time (VEC=4: 16 B-aligned vector access) or one at a time.
+// loads in flight per lane: 16-bit rows move half the bytes per instruction, so they unroll twice as far
+// (index kernel, bf16, B = 8192 x D = 2048: 52.5 -> 47.2 us; fp32 prefers 2: 75.6 vs 78.9 us -- r02n)
 template <typename T, int VEC, typename Fn>
 __device__ __forceinline__ void for_row(int D, int tid, int nthreads, Fn fn) {
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 4 && sizeof(T) == 2) {
+#pragma unroll 4
+    for (int d = tid * 4; d < D; d += nthreads * 4) fn(d);
+  } else if constexpr (VEC == 4) {
 #pragma unroll 2
     for (int d = tid * 4; d < D; d += nthreads * 4) fn(d);   // two iterations of loads in flight per lane
   } else {
@@ -112,10 +117,16 @@ __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + lo
 //   whose negative is j (CSR inverse; NULL => p = j-1, the roll-by-one of loss.py:214-216).
 // No block barriers: all reductions are warp shuffles.  Pass 1 accumulates the dot products, pass 2
 // re-reads the (L1-resident) rows and writes both gradients, with <u,dU> and <v,dV> in closed form.
-constexpr int INDEX_ROWS_PER_CTA = 8;
+#ifndef JSD_INDEX_ROWS
+#define JSD_INDEX_ROWS 8
+#endif
+#ifndef JSD_INDEX_MINBLOCKS
+#define JSD_INDEX_MINBLOCKS (2048 / (32 * JSD_INDEX_ROWS) / 2)   // at least half of the SM's warp slots: <= 64 registers
+#endif
+constexpr int INDEX_ROWS_PER_CTA = JSD_INDEX_ROWS;
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(32 * INDEX_ROWS_PER_CTA)
+__global__ void __launch_bounds__(32 * INDEX_ROWS_PER_CTA, JSD_INDEX_MINBLOCKS)
 jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D, const int* __restrict__ neg_index,
                  const int* __restrict__ inv_ptr, const int* __restrict__ inv_idx, const float* __restrict__ t_dev,
                  float* __restrict__ coefp, float* __restrict__ partials, T* __restrict__ dF, T* __restrict__ dG,
@@ -560,9 +571,12 @@ struct NormBwdJob {
   const float* reduce_src;
   int reduce_n;
   float* reduce_out;
+  float acc_scale[2];          // > 0: acc[] holds UNSCALED sums (fused single-pass kernel); the kernel multiplies them
+                               // by gamma * tau * acc_scale in fp32.  0: acc[] is already scaled (staged path)
   int acc_slots;               // 0: a single local accumulator (acc[])
   int slot_bf16;               // the slots hold bf16 (partials pushed by the peers' dV contractions), not fp32
-  const float* slot[8];
+  const float* slot[8];        // job 0 (or the only job)
+  const float* slot1[8];       // job 1 of a two-job launch (same acc_slots)
   const int* wait_flags;       // null: no wait
   const int* wait_counter;
   int wait_count;
@@ -586,24 +600,26 @@ __device__ __forceinline__ float4 load_slot4(const float* slot, size_t off, bool
   return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
                      __uint_as_float(w.y & 0xFFFF0000u));
 }
-__device__ __forceinline__ float4 load_acc4(const NormBwdJob& job, const float* acc, size_t off) {
+__device__ __forceinline__ float4 load_acc4(const NormBwdJob& job, const float* acc, size_t off, bool second = false) {
   if (job.acc_slots <= 0) return __ldcs(reinterpret_cast<const float4*>(acc + off));
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int sl = 0; sl < 8; ++sl)
     if (sl < job.acc_slots) {
-      const float4 h = load_slot4(job.slot[sl], off, job.slot_bf16 != 0);
+      const float4 h = load_slot4(second ? job.slot1[sl] : job.slot[sl], off, job.slot_bf16 != 0);
       g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
     }
   return g;
 }
-__device__ __forceinline__ float load_acc1(const NormBwdJob& job, const float* acc, size_t off) {
+__device__ __forceinline__ float load_acc1(const NormBwdJob& job, const float* acc, size_t off, bool second = false) {
   if (job.acc_slots <= 0) return acc[off];
   float g = 0.f;
 #pragma unroll
   for (int sl = 0; sl < 8; ++sl)
-    if (sl < job.acc_slots)
-      g += job.slot_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(job.slot[sl])[off]) : job.slot[sl][off];
+    if (sl < job.acc_slots) {
+      const float* sp = second ? job.slot1[sl] : job.slot[sl];
+      g += job.slot_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(sp)[off]) : sp[off];
+    }
   return g;
 }
 
@@ -625,6 +641,8 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   if (row < rows) {
   const float gamma = gamma_dev ? *gamma_dev : 1.f;
   const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
+  const float asel = second ? job.acc_scale[1] : job.acc_scale[0];
+  const float as = asel > 0.f ? gamma * expf(*t_dev) * asel : 1.f;      // x * 1 is exact: the staged path is unchanged
   const float inv = inv_norm[row];
   const T* x = X + (size_t)row * D;
   const size_t aoff = (size_t)row * D;
@@ -632,10 +650,11 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   float dot = 0.f;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
-      const float4 f = Vec4<T>::load(x + d), g = load_acc4(job, acc, aoff + d), q = Vec4<__nv_bfloat16>::load(pr + d);
-      dot += f.x * fmaf(c, q.x, g.x) + f.y * fmaf(c, q.y, g.y) + f.z * fmaf(c, q.z, g.z) + f.w * fmaf(c, q.w, g.w);
+      const float4 f = Vec4<T>::load(x + d), g = load_acc4(job, acc, aoff + d, second), q = Vec4<__nv_bfloat16>::load(pr + d);
+      dot += f.x * fmaf(c, q.x, g.x * as) + f.y * fmaf(c, q.y, g.y * as) + f.z * fmaf(c, q.z, g.z * as) +
+             f.w * fmaf(c, q.w, g.w * as);
     } else {
-      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), load_acc1(job, acc, aoff + d));
+      dot += to_f32(x[d]) * fmaf(c, __bfloat162float(pr[d]), load_acc1(job, acc, aoff + d, second) * as);
     }
   });
   dot = warp_sum(dot) * inv;   // <u, dU>
@@ -646,15 +665,15 @@ normalize_bwd_kernel(const NormBwdJob job, int rows, int D, const float* __restr
   T* o = dX + (size_t)row * D;
   for_row<T, VEC>(D, lane, 32, [&](int d) {
     if constexpr (VEC == 4) {
-      const float4 f = Vec4<T>::load(x + d), g = load_acc4(job, acc, aoff + d), q = Vec4<__nv_bfloat16>::load(pr + d);
+      const float4 f = Vec4<T>::load(x + d), g = load_acc4(job, acc, aoff + d, second), q = Vec4<__nv_bfloat16>::load(pr + d);
       float4 r;
-      r.x = (fmaf(c, q.x, g.x) - f.x * inv * dot) * inv;
-      r.y = (fmaf(c, q.y, g.y) - f.y * inv * dot) * inv;
-      r.z = (fmaf(c, q.z, g.z) - f.z * inv * dot) * inv;
-      r.w = (fmaf(c, q.w, g.w) - f.w * inv * dot) * inv;
+      r.x = (fmaf(c, q.x, g.x * as) - f.x * inv * dot) * inv;
+      r.y = (fmaf(c, q.y, g.y * as) - f.y * inv * dot) * inv;
+      r.z = (fmaf(c, q.z, g.z * as) - f.z * inv * dot) * inv;
+      r.w = (fmaf(c, q.w, g.w * as) - f.w * inv * dot) * inv;
       Vec4<T>::store(o + d, r);
     } else {
-      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), load_acc1(job, acc, aoff + d)) - to_f32(x[d]) * inv * dot) * inv);
+      o[d] = from_f32<T>((fmaf(c, __bfloat162float(pr[d]), load_acc1(job, acc, aoff + d, second) * as) - to_f32(x[d]) * inv * dot) * inv);
     }
   });
   }  // row < rows
@@ -719,6 +738,8 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
   const int D = nch * 128;
   const float gamma = gamma_dev ? *gamma_dev : 1.f;
   const float c = gdiag ? gamma * expf(*t_dev) * inv_rows * gdiag[row] : 0.f;
+  const float asel = second ? job.acc_scale[1] : job.acc_scale[0];
+  const float as = asel > 0.f ? gamma * expf(*t_dev) * asel : 1.f;      // x * 1 is exact: the staged path is unchanged
   const float inv = inv_norm[row];
   const T* x = X + (size_t)row * D + lane * 4;
   const size_t aoff = (size_t)row * D + lane * 4;
@@ -743,7 +764,8 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
 #pragma unroll
         for (int s = 0; s < 4; ++s)
           if (s0 + s < job.acc_slots) {
-            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(job.slot[s0 + s]) + aoff;
+            const __nv_bfloat16* a =
+                reinterpret_cast<const __nv_bfloat16*>(second ? job.slot1[s0 + s] : job.slot[s0 + s]) + aoff;
 #pragma unroll
             for (int i = 0; i < ROW_REG_CHUNKS; ++i)
               if (i < nch) raw[s][i] = __ldcs(reinterpret_cast<const uint2*>(a + i * 128));
@@ -776,7 +798,9 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
           if (s0 + s < job.acc_slots) {
 #pragma unroll
             for (int i = 0; i < ROW_REG_CHUNKS; ++i)
-              if (i < nch) h[s][i] = __ldcs(reinterpret_cast<const float4*>(job.slot[s0 + s] + aoff + i * 128));
+              if (i < nch)
+                h[s][i] = __ldcs(reinterpret_cast<const float4*>((second ? job.slot1[s0 + s] : job.slot[s0 + s]) + aoff +
+                                                                 i * 128));
           }
 #pragma unroll
         for (int s = 0; s < 2; ++s)
@@ -795,7 +819,8 @@ normalize_bwd_reg_kernel(const NormBwdJob job, int rows, int nch, const float* _
     if (i < nch) {
       xv[i] = Vec4<T>::load(x + i * 128);
       const float4 q = Vec4<__nv_bfloat16>::load(pr + i * 128);
-      dv[i] = make_float4(fmaf(c, q.x, dv[i].x), fmaf(c, q.y, dv[i].y), fmaf(c, q.z, dv[i].z), fmaf(c, q.w, dv[i].w));   // dU
+      dv[i] = make_float4(fmaf(c, q.x, dv[i].x * as), fmaf(c, q.y, dv[i].y * as), fmaf(c, q.z, dv[i].z * as),
+                          fmaf(c, q.w, dv[i].w * as));   // dU
     }
   float dot = 0.f;
 #pragma unroll

@@ -228,6 +228,63 @@ def dense_forward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, want_grad: 
     return out4, loss, (u, v, inv_f, inv_g, gmat, gdiag)
 
 
+FUSED_AUTO_MAX_BATCH = 4096
+
+
+def fused_supported(b: int, d: int) -> bool:
+    """The single-pass fused kernel (score tile and gradient accumulators resident in TMEM, no B x B buffer in HBM)
+    takes D in {64, 128, 192, 256}.  It is bound by the softplus / sigmoid epilogue (two score tiles are recomputed
+    for the text side), so by default it is used where it measures faster than the staged path -- B <= 4096 (1.1x there, 1.4-1.5x at
+    BASELINE configs[1]'s B = 1024 (profiles/fused_ab_*.log); JSD_FUSED=1 forces it wherever it is
+    supported (no O(B^2) memory: B = 65536, D = 128 needs 67 MB of accumulators instead of an 8.6 GB sigma matrix),
+    JSD_FUSED=0 disables it."""
+    import os
+    mode = os.environ.get("JSD_FUSED", "auto")
+    if mode == "0" or not _lib.load().jsd_dense_fused_supported(b, d):
+        return False
+    return mode == "1" or b <= FUSED_AUTO_MAX_BATCH
+
+
+def dense_fused_forward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor):
+    """Whole forward AND the tensor-core part of the backward in ONE library call (D <= 256).  Returns
+    (out4, loss, saved) with saved = (u, v, inv_f, inv_g, acc, gdiag) for dense_fused_backward."""
+    b, d = f.shape
+    dev = f.device
+    tt = _scalar(t, "temperature")
+    uv = torch.empty(2, b, d, dtype=torch.bfloat16, device=dev)
+    with _on_device(dev):
+        ns = _lib.load().jsd_dense_fused_splits(b, d)
+    acc = torch.empty(2, ns, b, d, dtype=torch.float32, device=dev)
+    small = torch.empty(3 * b + 8, dtype=torch.float32, device=dev)
+    inv_f, inv_g, gdiag = small[:b], small[b:2 * b], small[2 * b:3 * b]
+    out4, loss = small[3 * b:3 * b + 4], small[3 * b + 4]
+    with _on_device(dev):
+        ws = dense_workspace(dev)
+        _lib.call("jsd_dense_fused_forward", f.data_ptr(), g.data_ptr(), _code(f), b, d, tt.data_ptr(),
+                  uv[0].data_ptr(), uv[1].data_ptr(), inv_f.data_ptr(), inv_g.data_ptr(), acc[0].data_ptr(),
+                  acc[1].data_ptr(), gdiag.data_ptr(), ws.data_ptr(), out4.data_ptr(), loss.data_ptr(), _stream())
+    return out4, loss, (uv[0], uv[1], inv_f, inv_g, acc, gdiag)
+
+
+def dense_fused_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor, saved):
+    """Both normalisation Jacobians (+ dL/dt) on the fused kernel's accumulators: one launch.  Returns (dF, dG, dt)."""
+    u, v, inv_f, inv_g, acc, gdiag = saved
+    b, d = f.shape
+    dev = f.device
+    tt = _scalar(t, "temperature")
+    gg = _scalar(gamma, "gamma")
+    df = torch.empty_like(f)
+    dg = torch.empty_like(g)
+    small = torch.empty(b + 1, dtype=torch.float32, device=dev)       # row dots | dt
+    with _on_device(dev):
+        ws = dense_workspace(dev)
+        _lib.call("jsd_dense_fused_backward", f.data_ptr(), g.data_ptr(), _code(f), b, d, u.data_ptr(), v.data_ptr(),
+                  inv_f.data_ptr(), inv_g.data_ptr(), gdiag.data_ptr(), tt.data_ptr(), gg.data_ptr(),
+                  acc[0].data_ptr(), acc[1].data_ptr(), small.data_ptr(), ws.data_ptr(), df.data_ptr(),
+                  dg.data_ptr(), small[b:].data_ptr(), _stream())
+    return df, dg, small[b]
+
+
 def dense_backward(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, gamma: torch.Tensor, saved):
     """Whole single-GPU backward in ONE library call.  Returns (dF, dG, dt)."""
     u, v, inv_f, inv_g, gmat, gdiag = saved

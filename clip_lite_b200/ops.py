@@ -102,12 +102,21 @@ class _JSDIndexFn(torch.autograd.Function):
 
 
 class _JSDDenseFn(torch.autograd.Function):
+    """D in {64, 128, 192, 256}: the single-pass fused kernel computes the loss AND both gradient contractions in
+    the forward call (score tile, sigma(S) and the accumulators never leave the SM; nothing B x B is stored); the
+    backward only applies the upstream gradient and the normalisation Jacobians.  Other D: staged path (forward
+    writes the bf16 sigma matrix, backward runs the two contractions)."""
+
     @staticmethod
     def forward(ctx, f, g, t):
         need_grad = any(ctx.needs_input_grad)
         with torch.autocast("cuda", enabled=False):
             fc, gc = _common(f, g)
-            out4, loss, saved = K.dense_forward(fc, gc, t, want_grad=need_grad)
+            ctx.fused = need_grad and K.fused_supported(fc.shape[0], fc.shape[1])
+            if ctx.fused:
+                out4, loss, saved = K.dense_fused_forward(fc, gc, t)
+            else:
+                out4, loss, saved = K.dense_forward(fc, gc, t, want_grad=need_grad)
         if need_grad:
             ctx.save_for_backward(fc, gc, t, *saved)
         ctx.dtypes = (f.dtype, g.dtype, t.dtype)
@@ -118,7 +127,8 @@ class _JSDDenseFn(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_stats):
         fc, gc, t, *saved = ctx.saved_tensors
         with torch.autocast("cuda", enabled=False):
-            df, dg, dt = K.dense_backward(fc, gc, t, grad_loss, saved)
+            fn = K.dense_fused_backward if ctx.fused else K.dense_backward
+            df, dg, dt = fn(fc, gc, t, grad_loss, saved)
         fd, gd, td = ctx.dtypes
         return df.to(fd), dg.to(gd), dt.to(td)
 

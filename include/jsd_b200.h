@@ -149,6 +149,35 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
                        float* rowdot, void* workspace, void* sk_workspace, void* dF, void* dG, float* dt_out,
                        jsd_stream_t stream);
 
+/* Fused single-pass forward + backward for D in {64, 128, 192, 256} (single GPU, M == N == B): ONE tensor-core
+ * launch in which each score tile stays in TMEM, sigma(S) goes through shared memory straight back into the tensor
+ * cores and the gradient accumulators stay in TMEM (2 x 128 + D <= 512 columns) -- neither S nor sigma(S) reaches
+ * HBM and no B x B buffer exists.  The text side runs as a second set of CTAs of the same launch with the
+ * modalities swapped (the score tiles are recomputed: 8 B^2 D executed FLOPs for 6 B^2 D algorithmic ones).
+ *   jsd_dense_fused_supported  1 iff (B, D) can take this path
+ *   jsd_dense_fused_splits     S = CTAs per 128-row block (1..8): small batches are cut along the other modality so
+ *                              that the launch fills the GPU; every accumulator below then has S slices
+ *   jsd_dense_fused_fwd_bwd    U, V [B, D] bf16 unit rows -> loss (out4 / loss_out as jsd_dense_fwd), gdiag [B],
+ *                              acc_u / acc_v [S, B, D] fp32 whose sum over S is the sum over the negatives of
+ *                              sigma(S_ij) v_j resp. u_i, NOT yet scaled (autograd has no upstream gradient when
+ *                              its forward runs)
+ *   jsd_dense_fused_forward    jsd_normalize_cast_pair + jsd_dense_fused_fwd_bwd in one call
+ *   jsd_dense_fused_backward   both Jacobians of F.normalize in one launch: applies gamma tau / (B (B - 1)) to the
+ *                              accumulators and adds the positive-pair term in fp32, dt_out = gamma * dL/dt
+ * workspace = jsd_dense_workspace_bytes() bytes, as for jsd_dense_fwd. */
+int jsd_dense_fused_supported(int64_t B, int64_t D);
+int jsd_dense_fused_splits(int64_t B, int64_t D);
+int jsd_dense_fused_fwd_bwd(const void* U_bf16, const void* V_bf16, int64_t B, int64_t D, const float* t_dev,
+                            float* acc_u, float* acc_v, float* gdiag, void* workspace, float* out4, float* loss_out,
+                            jsd_stream_t stream);
+int jsd_dense_fused_forward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const float* t_dev,
+                            void* U_bf16, void* V_bf16, float* inv_f, float* inv_g, float* acc_u, float* acc_v,
+                            float* gdiag, void* workspace, float* out4, float* loss_out, jsd_stream_t stream);
+int jsd_dense_fused_backward(const void* F, const void* G, int dtype, int64_t B, int64_t D, const void* U_bf16,
+                             const void* V_bf16, const float* inv_f, const float* inv_g, const float* gdiag,
+                             const float* t_dev, const float* gamma_dev, const float* acc_u, const float* acc_v,
+                             float* rowdot, void* workspace, void* dF, void* dG, float* dt_out, jsd_stream_t stream);
+
 /* Row-slab (multi-GPU) convenience calls: one FFI crossing each.
  *   jsd_normalize_cast_pair       = jsd_normalize_cast of F and of G in one launch
  *   jsd_dense_backward_image_side = jsd_dense_bwd_du, jsd_normalize_bwd (positives at column row_offset + i of

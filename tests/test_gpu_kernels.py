@@ -246,6 +246,84 @@ def test_dense_bwd_stage(K, m, n, d, off):
     assert relerr(dv, ref["dv_acc"]) < 5e-3
 
 
+# ------------------------------------------------------------------ fused single-pass kernel (D <= 256)
+@pytest.mark.parametrize("b,d", [(128, 64), (256, 128), (200, 64), (1000, 256), (1024, 128), (333, 192),
+                                  (2, 64), (129, 128), (4096, 256), (8192, 128)])
+def test_dense_fused_stage(K, b, d):
+    """Score tile, sigma(S) and both gradient accumulators never leave the SM: loss, gdiag and the UNSCALED
+    accumulators sum_j sigma(S_ij) v_j / sum_i sigma(S_ij) u_i against the fp64 restatement on the same bf16
+    operands, and against the staged path (forward + two contractions through the bf16 Gmat)."""
+    from clip_lite_b200 import _lib
+    assert _lib.load().jsd_dense_fused_supported(b, d)
+    ns = _lib.load().jsd_dense_fused_splits(b, d)
+    assert 1 <= ns <= 8
+    u, v = _unit_bf16(b, d, seed=b + d)
+    t = dev_t()
+    acc = torch.full((2, ns, b, d), float("nan"), device="cuda")
+    gdiag = torch.empty(b, device="cuda")
+    out4 = torch.empty(4, device="cuda")
+    loss = torch.empty((), device="cuda")
+    ws = K.dense_workspace(u.device)
+    _lib.call("jsd_dense_fused_fwd_bwd", u.data_ptr(), v.data_ptr(), b, d, t.data_ptr(), acc[0].data_ptr(),
+              acc[1].data_ptr(), gdiag.data_ptr(), ws.data_ptr(), out4.data_ptr(), loss.data_ptr(), K._stream())
+    torch.cuda.synchronize()
+    ref = orc.dense_from_unit(u.double(), v.double(), T0)
+    assert torch.equal(loss, out4[2])
+    assert relerr(out4[0], ref["pos"]) < 1e-4
+    assert relerr(out4[1], ref["neg"]) < 1e-4
+    assert relerr(out4[2], ref["loss"]) < 1e-4
+    assert relerr(gdiag, ref["gdiag"]) < 1e-4
+    ref_u = ref["gmat"] @ v.double()                 # gmat: sigma(S) with 0 on the positives
+    ref_v = ref["gmat"].t() @ u.double()
+    assert torch.isfinite(acc).all()
+    acc_s = acc.double().sum(1)                      # the column splits' slices
+    assert relerr(acc_s[0], ref_u) < 5e-3            # sigma is rounded to bf16 before the second contraction
+    assert relerr(acc_s[1], ref_v) < 5e-3
+    if b >= 128:
+        # the staged path rounds (nearly) the same sigma values to bf16: the two routes agree far inside the tolerance
+        _, _, gmat, gd2 = K.dense_fwd(u, v, t)
+        one = torch.ones((), device="cuda")
+        scale = float(np.exp(T0)) / (b * (b - 1))
+        du = K.dense_bwd_du(gmat, v, t, one) / scale
+        dv = K.dense_bwd_dv(gmat, u, b, t, one) / scale
+        assert relerr(acc_s[0], du) < 1e-3 and relerr(acc_s[1], dv) < 1e-3
+        assert relerr(gdiag, gd2) < 1e-6
+    # a second launch on the re-armed workspace gives bit-identical results (deterministic, tickets reset)
+    acc2 = torch.empty_like(acc)
+    out4b = torch.empty(4, device="cuda")
+    _lib.call("jsd_dense_fused_fwd_bwd", u.data_ptr(), v.data_ptr(), b, d, t.data_ptr(), acc2[0].data_ptr(),
+              acc2[1].data_ptr(), gdiag.data_ptr(), ws.data_ptr(), out4b.data_ptr(), loss.data_ptr(), K._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(acc, acc2) and torch.equal(out4, out4b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("b,d", [(256, 64), (1024, 128), (1000, 256), (640, 192)])
+def test_dense_fused_autograd_matches_staged_and_oracle(monkeypatch, dtype, b, d):
+    from clip_lite_b200 import ops
+    f, g = orc.synth_embeddings(b, d, seed=5, correlated=True)
+    f, g = f.to(dtype), g.to(dtype)
+    # fp16: a GradScaler-sized upstream gradient keeps the B x D gradients out of fp16's subnormal range
+    gamma = 0.7 * (4096.0 if dtype == torch.float16 else 1.0)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("JSD_FUSED", mode)
+        fl, gl = f.cuda().requires_grad_(True), g.cuda().requires_grad_(True)
+        t = dev_t().requires_grad_(True)
+        loss, _ = ops.jsd_dense_loss(fl, gl, t)
+        (gamma * loss).backward()
+        res[mode] = (loss.detach(), fl.grad, gl.grad, t.grad)
+    rdf, rdg, rdt = orc.jsd_dense_grads(f.double(), g.double(), T0, gamma=gamma)
+    ref = orc.jsd_dense(f.double(), g.double(), T0)
+    for mode in ("1", "0"):
+        loss, df, dg, dt = res[mode]
+        assert relerr(loss, ref["loss"]) < LOSS_RTOL
+        assert relerr(df, rdf) < GRAD_RTOL and relerr(dg, rdg) < GRAD_RTOL and relerr(dt, rdt) < GRAD_RTOL
+    assert relerr(res["1"][0], res["0"][0]) < 1e-5
+    tol = {torch.float32: 1e-3, torch.bfloat16: 1e-2, torch.float16: 1e-2}[dtype]
+    assert relerr(res["1"][1], res["0"][1]) < tol and relerr(res["1"][2], res["0"][2]) < tol
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("b,d", [(128, 64), (256, 128), (1024, 128), (1024, 1024), (200, 72)])
 def test_dense_pipeline_vs_oracle(K, dtype, b, d):

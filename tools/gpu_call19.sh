@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_module.py -m gpu -x -q --timeout 300 -p no:cacheprovider > gpurun_out/r2p_pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2p_pytest.log | cut -c1-250
+timeout 300 python tools/fused_ab.py 2>&1 | tail -8 | tee gpurun_out/r2p_fused_ab.log

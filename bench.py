@@ -487,19 +487,24 @@ def run_b200(args, wl):
     slab_nocomm_ms = None
     if index_mode:
         # ---- roofline of the fused index kernel (HBM-bound): read F, G once, write dF, dG once
+        # (the fused call that also writes the gradients; an autograd step makes a loss-only call in the forward
+        #  -- reads F, G: 2 B D e bytes -- and this call, with the upstream gradient, in the backward: 6 B D e)
         with torch.no_grad():
             fd, gd, tc = f_dev.detach(), g_dev.detach(), t_dev.detach()
             for _ in range(3):
                 K.index_fwd_bwd(fd, gd, tc)
             k_ms = timed(lambda: K.index_fwd_bwd(fd, gd, tc), n_meas) / n_meas
+            f_ms = timed(lambda: K.index_fwd_bwd(fd, gd, tc, want_grad=False), n_meas) / n_meas
         alg_bytes = 4.0 * rows * dim * esize
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                     "traffic": _traffic(args.workload), "peak_source": peak_src,
-                    "kernel": "jsd_index_kernel (+ 1-block finalize), one call per step",
-                    "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": {"index_fwd_bwd": k_ms},
-                    "step_frac_of_peak": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs}
-        launches_per_step = 2
+                    "kernel": "jsd_index_kernel, gradient-writing call (+ 1-block finalize)",
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "launch_ms": {"index_fwd_bwd": k_ms, "index_fwd_only": f_ms},
+                    "step_algorithmic_bytes": 6.0 * rows * dim * esize,
+                    "step_frac_of_peak": 6.0 * rows * dim * esize / (ms_per_step * 1e-3) / 1e9 / peak_gbs}
+        launches_per_step = 4             # two calls (forward / backward), index kernel + finalize each
         tflops = None
     else:
         # ---- roofline of the dominant kernel family (the three tcgen05 GEMM launches of a step),
@@ -514,12 +519,26 @@ def run_b200(args, wl):
                 v_all = v
             gamma = torch.ones((), device=dev)
             t_c = t_dev.detach()
-            _, _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
-            stages = {
-                "fwd": lambda: K.dense_fwd(u, v_all, t_c, row_offset=rank * rows),
-                "bwd_du": lambda: K.dense_bwd_du(gmat, v_all, t_c, gamma),
-                "bwd_dv": lambda: K.dense_bwd_dv(gmat, u, batch, t_c, gamma),
-            }
+            fused = world == 1 and K.fused_supported(rows, dim)
+            if fused:
+                # D <= 256: ONE tensor-core launch computes the loss and both gradient contractions
+                from clip_lite_b200 import _lib as L
+                ns = L.load().jsd_dense_fused_splits(rows, dim)
+                acc = torch.empty(2, ns, rows, dim, dtype=torch.float32, device=dev)
+                gd_ = torch.empty(rows, dtype=torch.float32, device=dev)
+                o4 = torch.empty(5, dtype=torch.float32, device=dev)
+                wsf = K.dense_workspace(dev)
+                stages = {"fused_fwd_bwd": lambda: L.call(
+                    "jsd_dense_fused_fwd_bwd", u.data_ptr(), v.data_ptr(), rows, dim, t_c.data_ptr(),
+                    acc[0].data_ptr(), acc[1].data_ptr(), gd_.data_ptr(), wsf.data_ptr(), o4.data_ptr(),
+                    o4[4:].data_ptr(), torch.cuda.current_stream().cuda_stream)}
+            else:
+                _, _, gmat, _ = K.dense_fwd(u, v_all, t_c, row_offset=rank * rows)
+                stages = {
+                    "fwd": lambda: K.dense_fwd(u, v_all, t_c, row_offset=rank * rows),
+                    "bwd_du": lambda: K.dense_bwd_du(gmat, v_all, t_c, gamma),
+                    "bwd_dv": lambda: K.dense_bwd_dv(gmat, u, batch, t_c, gamma),
+                }
             stage_ms = {}
             for name, fn in stages.items():
                 for _ in range(3):
@@ -558,8 +577,10 @@ def run_b200(args, wl):
         achieved = 3 * flops_per_launch / (gemm_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": _traffic(args.workload) if world == 1 else None, "peak_source": peak_src,
-                    "kernel": "jsd_gemm_kernel (tcgen05, 3 launches/step: fwd, dU, dV)",
-                    "algorithmic_flops_per_launch": flops_per_launch,
+                    "kernel": ("jsd_fused_kernel (tcgen05, ONE launch/step: score tiles, sigma and both gradient "
+                               "accumulators stay on the SM; 3 x 2 B^2 D algorithmic FLOPs, 8 B^2 D executed)") if fused
+                              else "jsd_gemm_kernel (tcgen05, 3 launches/step: fwd, dU, dV)",
+                    "algorithmic_flops_per_launch": (3 if fused else 1) * flops_per_launch,
                     "launch_ms": stage_ms,
                     "step_frac_of_peak": 3 * flops_per_launch / (ms_per_step * 1e-3) / 1e12 / peak_tf}
         # library launches per step: normalise pair (+push), forward (+ loss), dU, dV, image Jacobian (helper
@@ -568,6 +589,8 @@ def run_b200(args, wl):
         launches_per_step = 5 if (world == 1 and os.environ.get("JSD_OVERLAP", "1") == "0") else 6
         if world > 1 and args.route == "symmetric":
             launches_per_step = 8
+        if fused:
+            launches_per_step = 3         # normalise pair, fused kernel, both Jacobians (+ dL/dt) in one launch
         tflops = 6.0 * rows * batch * dim / (ms_per_step * 1e-3) / 1e12
 
     line = None

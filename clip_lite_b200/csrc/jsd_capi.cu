@@ -749,9 +749,48 @@ int jsd_dense_backward(const void* F, const void* G, int dtype, int64_t B, int64
   JSD_REQUIRE(dt_out && acc_u && acc_v && rowdot && workspace, "jsd_dense_backward: null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   const SplitPlan su = plan_split(B, D, B, sk_workspace, 0), sv = plan_split(B, D, B, sk_workspace, 1);
+  SideStream* side = side_stream();
+  // Small batches (B = 1024, D = 1024: 16 pair tiles per contraction, ~20 us per launch almost all of it fixed cost
+  // -- prologue, pipeline fill, un-overlapped epilogue): both contractions fit on the GPU together, so they run
+  // SIDE BY SIDE (dV on the helper stream), then both Jacobians (+ dL/dt) in one launch.
+  {
+    const int cg = pick_cta_group(B);
+    const int64_t tiles = ((B + jsd::BLOCK_M * cg - 1) / (jsd::BLOCK_M * cg)) * ((D + jsd::BLOCK_N - 1) / jsd::BLOCK_N);
+    static int pair_small = -1;                                  // development knob: JSD_PAIRED=0 disables it
+    if (pair_small < 0) {
+      const char* e = getenv("JSD_PAIRED");
+      pair_small = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (pair_small && side != nullptr && su.ksplit == 1 && sv.ksplit == 1 && 2 * tiles * cg <= sm_count_cached()) {
+      JSD_CUDA_OK(cudaEventRecord(side->fork, st));
+      JSD_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      if (int rc = dense_bwd_common(false, Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0))
+        return rc;
+      if (int rc = dense_bwd_common(true, Gmat, ldg, U, B, B, D, t_dev, gamma_dev, nullptr, acc_v,
+                                    (jsd_stream_t)side->stream, nullptr, 0))
+        return rc;
+      JSD_CUDA_OK(cudaEventRecord(side->join, side->stream));
+      JSD_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+      jsd::NormBwdJob job{};
+      job.X[0] = F;
+      job.X[1] = G;
+      job.inv_norm[0] = inv_f;
+      job.inv_norm[1] = inv_g;
+      job.acc[0] = acc_u;
+      job.acc[1] = acc_v;
+      job.partner[0] = (const __nv_bfloat16*)V;
+      job.partner[1] = (const __nv_bfloat16*)U;
+      job.dX[0] = dF;
+      job.dX[1] = dG;
+      job.rowdot = rowdot;
+      job.ticket = dt_ticket(workspace);
+      job.dt_out = dt_out;
+      const float inv_rows = (float)(1.0 / (double)B);
+      JSD_DISPATCH_DTYPE(dtype, (launch_normalize_bwd<T>(job, 2, B, D, gdiag, t_dev, gamma_dev, inv_rows, st)));
+    }
+  }
   if (int rc = dense_bwd_common(false, Gmat, ldg, V, B, B, D, t_dev, gamma_dev, nullptr, acc_u, stream, nullptr, 0, &su))
     return rc;
-  SideStream* side = side_stream();
   if (side != nullptr || su.ksplit > 1 || sv.ksplit > 1) {
     // image-side Jacobian (+ gamma * dL/dt) on the helper stream, next to the dV contraction.  The contraction
     // is enqueued FIRST so that its persistent CTAs take the SMs and the Jacobian's blocks fill in as they retire.

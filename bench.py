@@ -221,6 +221,9 @@ def time_cpu(wl, batch, dim, budget_s, steps=None, warmup=1):
                       f"{n_steps} steps after {warmup} warm-up (mean {mean*1e3:.1f} ms/step)"}, mean, rows
 
 
+_orig_time_cpu = time_cpu
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

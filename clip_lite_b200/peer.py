@@ -285,18 +285,19 @@ class _PeerSymmetricFn(torch.autograd.Function):
 
 
 def peer_dense_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, group=None,
-                    exchange: Optional[PeerExchange] = None, route: str = "reduce"):
+                    exchange: Optional[PeerExchange] = None, route: str = "reduce", partials: Optional[str] = None):
     """(L_r, stats) for this rank's rows against the text rows of every rank, exchanged over peer memory.
     route="reduce" (default, measured): dV partials are pulled and summed by the owners; route="symmetric": the
     image rows are exchanged as well and every rank recomputes its own column slab (no gradient traffic; needs
-    the same upstream gradient on every rank)."""
+    the same upstream gradient on every rank).  partials: "bf16" (default: the dV contraction pushes bf16 tiles into
+    the owners' memory while it runs) or "fp32" (exact to fp32, the owners pull) -- the same on every rank."""
     if route == "symmetric":
         ex_v = exchange if exchange is not None else get_exchange(f.shape[0], f.shape[1], group)
         ex_u = get_exchange(f.shape[0], f.shape[1], group, tag="image")
         return _PeerSymmetricFn.apply(f, g, t, ex_v, ex_u)
     if route != "reduce":
         raise ValueError(f"route must be 'reduce' or 'symmetric', got {route!r}")
-    ex = exchange if exchange is not None else get_exchange(f.shape[0], f.shape[1], group)
+    ex = exchange if exchange is not None else get_exchange(f.shape[0], f.shape[1], group, partials=partials)
     return _PeerDenseFn.apply(f, g, t, ex)
 
 

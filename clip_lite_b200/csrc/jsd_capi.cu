@@ -204,12 +204,50 @@ int launch_gemm_any(bool a_mn, bool b_mn, int cg, const CUtensorMap& tmA, const 
 
 bool fits_int(int64_t v) { return v > 0 && v < (int64_t)1 << 30; }
 
+// JSD_INDEX_RING=0 sends the normal mode through the L1-based kernel as well (A/B timing)
+bool index_ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JSD_INDEX_RING");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <typename T>
 int launch_index(const void* F, const void* G, int64_t B, int64_t D, const int32_t* neg, const int32_t* iptr,
                  const int32_t* iidx, const float* t_dev, float* coefp, float* partials, void* dF, void* dG,
-                 float grad_scale, const float* gamma_dev, cudaStream_t st) {
+                 float grad_scale, const float* gamma_dev, cudaStream_t st, int* n_partials) {
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(G) |
                                      reinterpret_cast<uintptr_t>(dF) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0;
+  *n_partials = (int)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA);
+  // normal (roll-by-one) pairing on 16-byte-granular rows: persistent CTAs, rows staged once through shared-memory
+  // rings by the bulk-copy engine
+  const size_t row_bytes = (size_t)D * sizeof(T);
+  // (long rows only: with 1 KB rows the per-row barrier round trips of eight consumer warps dominate -- 204 vs 95 us
+  //  at 65536 x 512 bf16; at 8 KB rows the ring wins 75.6 -> 58.4 us per call, r02s)
+  if (neg == nullptr && vec && row_bytes % 16 == 0 && row_bytes >= 8192 && index_ring_enabled()) {
+    int slots = (int)((size_t)(196 * 1024) / (2 * row_bytes));
+    if (slots > jsd::IR_MAX_SLOTS) slots = jsd::IR_MAX_SLOTS;
+    const int sms = sm_count_cached();
+    if (slots >= 4 && sms > 0) {
+      const size_t smem = 2 * (size_t)slots * row_bytes;
+      auto kern = jsd::jsd_index_ring_kernel<T>;
+      static unsigned long long configured_mask = 0;
+      int dev = 0;
+      JSD_CUDA_OK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !((configured_mask >> dev) & 1ull)) {
+        JSD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev >= 0 && dev < 64) configured_mask |= 1ull << dev;
+      }
+      const int grid = (int)(B < sms ? B : sms);
+      kern<<<grid, jsd::IR_THREADS, smem, st>>>((const T*)F, (const T*)G, (int)B, (int)D, slots, t_dev, partials,
+                                                (T*)dF, (T*)dG, grad_scale, gamma_dev);
+      JSD_CUDA_OK(cudaGetLastError());
+      *n_partials = grid;
+      return 0;
+    }
+  }
   const unsigned grid = (unsigned)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA);
   const int threads = 32 * jsd::INDEX_ROWS_PER_CTA;
   if (vec)
@@ -425,14 +463,14 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
   cudaStream_t st = (cudaStream_t)stream;
   float* coefp = (float*)workspace;
   float* partials = coefp + B;
+  int n_partials = 0;
   int rc = [&]() -> int {
     JSD_DISPATCH_DTYPE(dtype, (launch_index<T>(F, G, B, D, neg_index, inv_ptr, inv_idx, t_dev, coefp, partials, dF,
-                                               dG, grad_scale, gamma_dev, st)));
+                                               dG, grad_scale, gamma_dev, st, &n_partials)));
   }();
   if (rc) return rc;
-  jsd::finalize_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>(
-      partials, (int)((B + jsd::INDEX_ROWS_PER_CTA - 1) / jsd::INDEX_ROWS_PER_CTA), 3, 1.0 / (double)B, 1.0 / (double)B, 1.0, 0.0, out4,
-                                          loss_out);
+  jsd::finalize_kernel<<<1, jsd::FINALIZE_THREADS, 0, st>>>(partials, n_partials, 3, 1.0 / (double)B, 1.0 / (double)B,
+                                                             1.0, 0.0, out4, loss_out);
   JSD_CUDA_OK(cudaGetLastError());
   return 0;
 }

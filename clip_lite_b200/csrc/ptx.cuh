@@ -202,6 +202,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy global -> shared, completion (bytes) signalled on an mbarrier: `bytes` a multiple of 16, both
+// addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 // 1-D bulk copy shared -> global (bulk async group): `bytes` a multiple of 16, both addresses 16-byte aligned.
 // The destination may be peer memory: the copy leaves the SM as full-size packets, no LSU involvement.
 __device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {

@@ -58,6 +58,15 @@ SIGNATURES = {
     "jsd_normalize_bwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "jsd_ln_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "jsd_ln_normalize_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_float,
+                                      c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    "jsd_ln_normalize_bwd_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float,
+                                          c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]),
     "jsd_peer_flag_bytes": (c_size_t, []),
     "jsd_peer_alloc": (c_int, [c_size_t, c_void_p]),
     "jsd_peer_free": (c_int, [c_void_p]),
@@ -97,7 +106,7 @@ class PeerCtx(ctypes.Structure):
                 ("flags", c_void_p * MAX_PEERS)]
 
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 _lib = None
 
 

@@ -8,7 +8,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libjsd_b200.so")
 SOURCES = ["jsd_capi.cu"]
-HEADERS = ["ptx.cuh", "jsd_dense.cuh", "jsd_fused.cuh", "jsd_rowwise.cuh", "jsd_score.cuh",
+HEADERS = ["ptx.cuh", "jsd_dense.cuh", "jsd_fused.cuh", "jsd_heads.cuh", "jsd_rowwise.cuh", "jsd_score.cuh",
            os.path.join("..", "..", "include", "jsd_b200.h")]
 
 NVCC_FLAGS = [

@@ -9,6 +9,7 @@
 
 #include "jsd_dense.cuh"
 #include "jsd_fused.cuh"
+#include "jsd_heads.cuh"
 #include "jsd_rowwise.cuh"
 #include "jsd_score.cuh"
 
@@ -442,7 +443,7 @@ int* dt_ticket(void* workspace) { return reinterpret_cast<int*>(workspace) + 1; 
 
 extern "C" {
 
-int jsd_abi_version(void) { return 11; }
+int jsd_abi_version(void) { return 12; }
 
 const char* jsd_last_error(void) { return g_err; }
 
@@ -1476,6 +1477,158 @@ int jsd_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
   p.ldo = N;
   return launch_gemm_any<jsd::MODE_GRAD>(a_mn_major != 0, b_mn_major != 0, cg, tmA, tmB, p, sk_workspace,
                                           (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+/* ------------------------------------------------------------------ projection-head tail (LayerNorm + normalise) */
+namespace {
+
+// blocks of the fused LayerNorm / normalise backward: every block walks rows blockIdx.x, + gridDim.x, ... and keeps
+// the LayerNorm weight / bias sums of its rows in registers.  One wave of resident blocks (occupancy x SMs, at most
+// 8 per SM -- the bound the workspace is sized for), never more blocks than rows.
+constexpr int kLnBwdMaxBlocksPerSm = 8;
+int ln_bwd_block_cap(int64_t rows) {
+  const int64_t cap = kLnBwdMaxBlocksPerSm * (int64_t)(sm_count_cached() > 0 ? sm_count_cached() : 148);
+  return (int)(rows < cap ? rows : cap);
+}
+template <typename Kernel>
+int ln_bwd_blocks(Kernel kernel, int threads, int64_t rows) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  if (per_sm > kLnBwdMaxBlocksPerSm) per_sm = kLnBwdMaxBlocksPerSm;
+  const int64_t wave = (int64_t)per_sm * (sm_count_cached() > 0 ? sm_count_cached() : 148);
+  return (int)(rows < wave ? rows : wave);
+}
+
+template <typename T>
+int launch_ln_normalize(const jsd::LnNormJob& job, int count, int64_t rows, int64_t D, bool out_bf16, cudaStream_t st) {
+  uintptr_t bits = 0;
+  for (int i = 0; i < count; ++i)
+    bits |= reinterpret_cast<uintptr_t>(job.X[i]) | reinterpret_cast<uintptr_t>(job.out[i]) |
+            reinterpret_cast<uintptr_t>(job.w[i]) | reinterpret_cast<uintptr_t>(job.b[i]);
+  const int variant = jsd::ln_fwd_variant(D, (bits & 15) == 0);
+  const dim3 grid((unsigned)((rows + 7) / 8), (unsigned)count);
+  auto go = [&](auto kernel, int arg) { kernel<<<grid, 256, 0, st>>>(job, (int)rows, arg); };
+  if (out_bf16) jsd::ln_fwd_select<T, __nv_bfloat16>(variant, D, go);
+  else jsd::ln_fwd_select<T, float>(variant, D, go);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int launch_ln_normalize_bwd(const jsd::LnNormBwdJob& job, int count, int64_t rows, int64_t D, const float* gdiag,
+                            const float* t_dev, const float* gamma_dev, float inv_rows, int* blocks_out,
+                            cudaStream_t st) {
+  uintptr_t bits = (uintptr_t)job.slice_stride * 4u | reinterpret_cast<uintptr_t>(job.col_partials);
+  for (int i = 0; i < count; ++i)
+    bits |= reinterpret_cast<uintptr_t>(job.X[i]) | reinterpret_cast<uintptr_t>(job.dX[i]) |
+            reinterpret_cast<uintptr_t>(job.acc[i]) | reinterpret_cast<uintptr_t>(job.partner[i]);
+  const jsd::LnBwdPlan plan = jsd::ln_bwd_plan(D, (bits & 15) == 0);
+  JSD_REQUIRE(plan.kch > 0, "LayerNorm/normalise backward: D=%lld too large (max %d%s)", (long long)D,
+              jsd::LN_BWD_MAX_KCH * jsd::LN_BWD_THREADS * plan.vec, plan.vec == 4 ? "" : " for unaligned rows");
+  jsd::ln_bwd_select<T>(plan, [&](auto kernel) {
+    const int blocks = ln_bwd_blocks(kernel, plan.threads, rows);
+    *blocks_out = blocks;
+    kernel<<<dim3((unsigned)blocks, (unsigned)count), plan.threads, 0, st>>>(job, (int)rows, (int)D, gdiag, t_dev,
+                                                                              gamma_dev, inv_rows);
+  });
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t jsd_ln_workspace_bytes(int64_t rows, int64_t D) {
+  if (rows <= 0 || D <= 0) return 0;
+  return (size_t)2 * (size_t)ln_bwd_block_cap(rows) * 2 * (size_t)D * sizeof(float);
+}
+
+int jsd_ln_normalize_pair(const void* X0, const void* X1, int dtype, int64_t rows, int64_t D, const float* w0,
+                          const float* b0, float eps0, const float* w1, const float* b1, float eps1, int out_bf16,
+                          void* out0, void* out1, float* stats0, float* stats1, jsd_stream_t stream) {
+  JSD_REQUIRE(X0 && out0 && stats0, "jsd_ln_normalize_pair: null pointer argument");
+  JSD_REQUIRE((X1 == nullptr) == (out1 == nullptr) && (X1 == nullptr) == (stats1 == nullptr),
+              "jsd_ln_normalize_pair: X1, out1 and stats1 must be given together");
+  JSD_REQUIRE(fits_int(rows) && fits_int(D), "jsd_ln_normalize_pair: rows=%lld, D=%lld out of range", (long long)rows,
+              (long long)D);
+  JSD_REQUIRE(eps0 >= 0.f && eps1 >= 0.f, "jsd_ln_normalize_pair: negative eps");
+  jsd::LnNormJob job{};
+  job.X[0] = X0; job.w[0] = w0; job.b[0] = b0; job.out[0] = out0; job.eps[0] = eps0;
+  job.mean[0] = stats0; job.rstd[0] = stats0 + rows; job.inv_norm[0] = stats0 + 2 * rows;
+  const int count = X1 ? 2 : 1;
+  if (X1) {
+    job.X[1] = X1; job.w[1] = w1; job.b[1] = b1; job.out[1] = out1; job.eps[1] = eps1;
+    job.mean[1] = stats1; job.rstd[1] = stats1 + rows; job.inv_norm[1] = stats1 + 2 * rows;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  JSD_DISPATCH_DTYPE(dtype, (launch_ln_normalize<T>(job, count, rows, D, out_bf16 != 0, st)));
+}
+
+int jsd_ln_normalize_bwd_pair(const void* X0, const void* X1, int dtype, int64_t rows, int64_t D, const float* w0,
+                              const float* b0, const float* w1, const float* b1, const float* stats0,
+                              const float* stats1, const float* acc0, const float* acc1, int64_t n_slices,
+                              int64_t slice_stride, float acc_scale, const void* partner0_bf16,
+                              int64_t partner_offset0, const void* partner1_bf16, int64_t partner_offset1,
+                              const float* gdiag, const float* t_dev, const float* gamma_dev, int64_t M_rows,
+                              void* workspace, void* dX0, void* dX1, float* dw0, float* db0, float* dw1, float* db1,
+                              float* rowdot, float* dt_out, jsd_stream_t stream) {
+  JSD_REQUIRE(X0 && stats0 && acc0 && dX0 && workspace, "jsd_ln_normalize_bwd_pair: null pointer argument");
+  const bool two = X1 != nullptr;
+  JSD_REQUIRE(!two || (stats1 && acc1 && dX1), "jsd_ln_normalize_bwd_pair: second row set is incomplete");
+  JSD_REQUIRE(fits_int(rows) && fits_int(D) && M_rows > 0, "jsd_ln_normalize_bwd_pair: bad shape");
+  JSD_REQUIRE(n_slices >= 1 && n_slices <= 64 && (n_slices == 1 || slice_stride >= rows * D),
+              "jsd_ln_normalize_bwd_pair: bad accumulator slices (%lld, stride %lld)", (long long)n_slices,
+              (long long)slice_stride);
+  JSD_REQUIRE(acc_scale >= 0.f, "jsd_ln_normalize_bwd_pair: negative acc_scale");
+  JSD_REQUIRE(gdiag == nullptr || (partner0_bf16 && (!two || partner1_bf16) && t_dev),
+              "jsd_ln_normalize_bwd_pair: the positive-pair term needs partner rows and the temperature");
+  JSD_REQUIRE(acc_scale == 0.f || t_dev, "jsd_ln_normalize_bwd_pair: acc_scale needs the temperature");
+  JSD_REQUIRE(dt_out == nullptr || rowdot != nullptr, "jsd_ln_normalize_bwd_pair: dt_out needs rowdot");
+  jsd::LnNormBwdJob job{};
+  job.X[0] = X0; job.w[0] = w0; job.b[0] = b0;
+  job.mean[0] = stats0; job.rstd[0] = stats0 + rows; job.inv_norm[0] = stats0 + 2 * rows;
+  job.acc[0] = acc0; job.partner[0] = (const __nv_bfloat16*)partner0_bf16; job.partner_offset[0] = partner_offset0;
+  job.dX[0] = dX0;
+  if (two) {
+    job.X[1] = X1; job.w[1] = w1; job.b[1] = b1;
+    job.mean[1] = stats1; job.rstd[1] = stats1 + rows; job.inv_norm[1] = stats1 + 2 * rows;
+    job.acc[1] = acc1; job.partner[1] = (const __nv_bfloat16*)partner1_bf16; job.partner_offset[1] = partner_offset1;
+    job.dX[1] = dX1;
+  }
+  job.slice_stride = n_slices > 1 ? slice_stride : 0;
+  job.n_slices = (int)n_slices;
+  job.acc_scale = acc_scale;
+  job.col_partials = (float*)workspace;
+  job.rowdot = rowdot;
+  const int count = two ? 2 : 1;
+  const float inv_rows = (float)(1.0 / (double)M_rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 1, blocks = 0;
+  switch (dtype) {
+    case JSD_F32: rc = launch_ln_normalize_bwd<float>(job, count, rows, D, gdiag, t_dev, gamma_dev, inv_rows, &blocks, st); break;
+    case JSD_BF16: rc = launch_ln_normalize_bwd<__nv_bfloat16>(job, count, rows, D, gdiag, t_dev, gamma_dev, inv_rows, &blocks, st); break;
+    case JSD_F16: rc = launch_ln_normalize_bwd<__half>(job, count, rows, D, gdiag, t_dev, gamma_dev, inv_rows, &blocks, st); break;
+    default: return fail("unsupported dtype code %d", dtype);
+  }
+  if (rc) return rc;
+  jsd::LnFinalizeJob fin{};
+  fin.col_partials = (const float*)workspace;
+  fin.nblocks = blocks;
+  fin.dw[0] = dw0; fin.db[0] = db0;
+  fin.dw[1] = two ? dw1 : nullptr; fin.db[1] = two ? db1 : nullptr;
+  fin.rowdot = rowdot;
+  fin.rows = (int)rows;
+  fin.dt_out = dt_out;
+  const dim3 fgrid((unsigned)((D + 255) / 256), (unsigned)(2 * count));
+  jsd::ln_bwd_finalize_kernel<<<fgrid, 256, 0, st>>>(fin, (int)D);
+  JSD_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -9,7 +9,11 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#ifdef JSD_HOST_EMU
+#include "ptx_emu.cuh"   // tests/emu: the kernels of this header run on the CPU under the test shim (tests only)
+#else
 #include "ptx.cuh"
+#endif
 
 namespace jsd {
 
@@ -295,6 +299,7 @@ jsd_index_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, int D,
   }
 }
 
+#ifndef JSD_HOST_EMU   // bulk-copy engine + mbarriers: not emulated
 // ------------------------------------------------------------------ index mode, normal (roll-by-one) pairing, staged
 // Same arithmetic as jsd_index_kernel, but every row of F and G is fetched from memory EXACTLY ONCE: persistent
 // CTAs own contiguous row ranges, a producer warp streams the rows through two shared-memory rings with the
@@ -454,6 +459,8 @@ jsd_index_ring_kernel(const T* __restrict__ F, const T* __restrict__ G, int B, i
   }
 }
 
+#endif  // !JSD_HOST_EMU
+
 // out4 = {pos, neg, pos + neg, dL/dt} (+ an optional separate copy of the loss); deterministic (fixed order, fp64).
 constexpr int FINALIZE_THREADS = 1024;
 
@@ -578,6 +585,7 @@ __device__ __forceinline__ void load8<__half>(const __half* p, float (&x)[8]) {
   }
 }
 
+#ifndef JSD_HOST_EMU   // bulk-copy engine + system-scope flags: not emulated
 // VEC = 8: D % 8 == 0 and 16-byte aligned rows (the product's shapes): every warp builds its bf16 unit row in shared
 // memory and ONE lane hands it to the bulk-copy engine once per destination (cp.async.bulk shared -> global, a
 // whole 2 KB row per instruction) -- per-lane 16-byte stores to 8 peers reach ~420 GB/s (trace r02j: 32-37 us for
@@ -665,6 +673,8 @@ normalize_push_kernel(const __grid_constant__ PeerPushJob job, int rows, int D) 
     if (threadIdx.x == 0) trace_event(TK_PUSH, TE_END);
   }
 }
+
+#endif  // !JSD_HOST_EMU
 
 // Fixed-order fp64 sum of n floats by one block (deterministic); every thread of the block must call it.
 __device__ __forceinline__ void block_reduce_to(const float* src, int n, float* out) {

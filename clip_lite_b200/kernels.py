@@ -375,6 +375,138 @@ def normalize_cast_pair(f: torch.Tensor, g: torch.Tensor):
     return uv[0], uv[1], inv[0], inv[1]
 
 
+def dense_fused_fwd_bwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor):
+    """The single-pass fused kernel on ready bf16 unit rows (D in {64, 128, 192, 256}).  Returns
+    (out4, loss, gdiag, acc) with acc fp32 [2, S, B, D]: the UNSCALED accumulators of the image / text side in S
+    column-split slices (jsd_dense_fused_splits)."""
+    _req(u, "U", dtype=torch.bfloat16, ndim=2)
+    _req(v, "V", dtype=torch.bfloat16, ndim=2)
+    if u.shape != v.shape:
+        raise ValueError("the fused kernel needs M == N == B")
+    b, d = u.shape
+    dev = u.device
+    tt = _scalar(t, "temperature")
+    lib = _lib.load()
+    if not lib.jsd_dense_fused_supported(b, d):
+        raise ValueError(f"the fused single-pass kernel does not take B={b}, D={d}")
+    with _on_device(dev):
+        ns = lib.jsd_dense_fused_splits(b, d)
+    acc = torch.empty(2, ns, b, d, dtype=torch.float32, device=dev)
+    small = torch.empty(b + 8, dtype=torch.float32, device=dev)
+    gdiag, out4, loss = small[:b], small[b:b + 4], small[b + 4]
+    with _on_device(dev):
+        ws = dense_workspace(dev)
+        _lib.call("jsd_dense_fused_fwd_bwd", u.data_ptr(), v.data_ptr(), b, d, tt.data_ptr(), acc[0].data_ptr(),
+                  acc[1].data_ptr(), gdiag.data_ptr(), ws.data_ptr(), out4.data_ptr(), loss.data_ptr(), _stream())
+    return out4, loss, gdiag, acc
+
+
+# ------------------------------------------------------------------ projection-head tail (LayerNorm + normalise)
+def _ln_param(p: Optional[torch.Tensor], d: int, name: str) -> Optional[torch.Tensor]:
+    if p is None:
+        return None
+    _req(p, name, ndim=1)
+    if p.numel() != d:
+        raise ValueError(f"{name} must have {d} entries, got {p.numel()}")
+    return p if p.dtype == torch.float32 else p.float()
+
+
+def ln_normalize_pair(x0: torch.Tensor, x1: Optional[torch.Tensor], ln0, ln1=None, out_bf16: bool = False):
+    """u = LN(x) / max(||LN(x)||, 1e-12) for one or two [rows, D] row sets of the same shape and dtype in one launch
+    (the image and the text head, reference loss.py:36-38 + :94-95).  ln = (weight or None, bias or None, eps).
+    Returns (out0, out1, stats0, stats1): unit rows in fp32 (bf16 with out_bf16) and stats [3, rows] fp32 =
+    mean | rstd | 1 / max(||LN(x)||, 1e-12); the second pair is None when x1 is None."""
+    _req(x0, "X0", ndim=2)
+    rows, d = x0.shape
+    if rows == 0 or d == 0:
+        raise ValueError("empty batch")
+    two = x1 is not None
+    if two:
+        _req(x1, "X1", dtype=x0.dtype, ndim=2)
+        if x1.shape != x0.shape:
+            raise ValueError(f"X0 {tuple(x0.shape)} and X1 {tuple(x1.shape)} must have the same shape")
+    w0, b0, e0 = _ln_param(ln0[0], d, "LayerNorm weight"), _ln_param(ln0[1], d, "LayerNorm bias"), float(ln0[2])
+    w1 = b1 = None
+    e1 = 0.0
+    if two:
+        w1, b1, e1 = _ln_param(ln1[0], d, "LayerNorm weight"), _ln_param(ln1[1], d, "LayerNorm bias"), float(ln1[2])
+    dev = x0.device
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    out = torch.empty(2 if two else 1, rows, d, dtype=odt, device=dev)
+    stats = torch.empty(2 if two else 1, 3, rows, dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        _lib.call("jsd_ln_normalize_pair", _ptr(x0), _ptr(x1), _code(x0), rows, d, _ptr(w0), _ptr(b0), e0, _ptr(w1),
+                  _ptr(b1), e1, int(out_bf16), out[0].data_ptr(), out[1].data_ptr() if two else None,
+                  stats[0].data_ptr(), stats[1].data_ptr() if two else None, _stream())
+    return (out[0], out[1], stats[0], stats[1]) if two else (out[0], None, stats[0], None)
+
+
+def ln_normalize_bwd_pair(x0: torch.Tensor, x1: Optional[torch.Tensor], ln0, ln1, stats0: torch.Tensor,
+                          stats1: Optional[torch.Tensor], acc0: torch.Tensor, acc1: Optional[torch.Tensor],
+                          acc_scale: float = 0.0, partner0: Optional[torch.Tensor] = None,
+                          partner1: Optional[torch.Tensor] = None, gdiag: Optional[torch.Tensor] = None,
+                          t: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None,
+                          m_rows: Optional[int] = None, want_dt: bool = False):
+    """Positive-pair term + Jacobian of F.normalize + LayerNorm backward in one pass (and one small reduction launch).
+    acc: fp32 [rows, D] or [S, rows, D] (S slices summed in order); see include/jsd_b200.h for the flavours.
+    Returns (dx0, dx1, dw0, db0, dw1, db1, dt): dx in x's dtype, dw / db fp32 [D] (None where the LayerNorm has no
+    such parameter), dt = sum_rows <u, dU> of row set 0 (None unless want_dt)."""
+    _req(x0, "X0", ndim=2)
+    rows, d = x0.shape
+    two = x1 is not None
+    dev = x0.device
+
+    def _acc(a, name):
+        _req(a, name, dtype=torch.float32)
+        if a.dim() == 2:
+            a = a.unsqueeze(0)
+        if a.dim() != 3 or a.shape[1:] != (rows, d):
+            raise ValueError(f"{name} must be [rows, D] or [S, rows, D] for rows={rows}, D={d}; got {tuple(a.shape)}")
+        return a
+
+    acc0 = _acc(acc0, "acc0")
+    ns = acc0.shape[0]
+    if two:
+        _req(x1, "X1", dtype=x0.dtype, ndim=2)
+        acc1 = _acc(acc1, "acc1")
+        if x1.shape != x0.shape or acc1.shape != acc0.shape:
+            raise ValueError("the two row sets must have the same shape and the same number of accumulator slices")
+    for st in (stats0,) + ((stats1,) if two else ()):
+        _req(st, "stats", dtype=torch.float32, ndim=2)
+        if st.shape != (3, rows):
+            raise ValueError(f"stats must be [3, {rows}], got {tuple(st.shape)}")
+    if gdiag is not None:
+        _req(gdiag, "gdiag", dtype=torch.float32, ndim=1)
+        for pr in (partner0,) + ((partner1,) if two else ()):
+            _req(pr, "partner", dtype=torch.bfloat16, ndim=2)
+            if pr.shape[1] != d or pr.shape[0] < rows:
+                raise ValueError("partner rows do not cover the row set")
+    w0, b0 = _ln_param(ln0[0], d, "LayerNorm weight"), _ln_param(ln0[1], d, "LayerNorm bias")
+    w1 = b1 = None
+    if two:
+        w1, b1 = _ln_param(ln1[0], d, "LayerNorm weight"), _ln_param(ln1[1], d, "LayerNorm bias")
+    tt = None if t is None else _scalar(t, "temperature")
+    gg = None if gamma is None else _scalar(gamma, "gamma")
+    dx = [torch.empty_like(x0), torch.empty_like(x1) if two else None]
+    dwb = torch.empty(4, d, dtype=torch.float32, device=dev)       # dw0 | db0 | dw1 | db1
+    small = torch.empty(rows + 1, dtype=torch.float32, device=dev) if want_dt else None   # row dots | dt
+    lib = _lib.load()
+    with _on_device(dev):
+        ws = torch.empty(lib.jsd_ln_workspace_bytes(rows, d) // 4, dtype=torch.float32, device=dev)
+        _lib.call("jsd_ln_normalize_bwd_pair", _ptr(x0), _ptr(x1), _code(x0), rows, d, _ptr(w0), _ptr(b0), _ptr(w1),
+                  _ptr(b1), _ptr(stats0), _ptr(stats1) if two else None, acc0.data_ptr(),
+                  acc1.data_ptr() if two else None, ns, acc0.stride(0) if ns > 1 else 0, float(acc_scale),
+                  _ptr(partner0) if gdiag is not None else None, 0,
+                  _ptr(partner1) if (gdiag is not None and two) else None, 0, _ptr(gdiag), _ptr(tt), _ptr(gg),
+                  int(m_rows if m_rows is not None else rows), ws.data_ptr(), dx[0].data_ptr(),
+                  dx[1].data_ptr() if two else None, dwb[0].data_ptr() if w0 is not None else None,
+                  dwb[1].data_ptr() if b0 is not None else None, dwb[2].data_ptr() if w1 is not None else None,
+                  dwb[3].data_ptr() if b1 is not None else None, small.data_ptr() if want_dt else None,
+                  small[rows:].data_ptr() if want_dt else None, _stream())
+    return (dx[0], dx[1], dwb[0] if w0 is not None else None, dwb[1] if b0 is not None else None,
+            dwb[2] if w1 is not None else None, dwb[3] if b1 is not None else None, small[rows] if want_dt else None)
+
+
 def dense_backward_image_side(f, v_all, inv_f, gmat, gdiag, t, gamma, row_offset: int):
     """dU GEMM + positive-pair term + normalisation Jacobian + dL/dt for a row slab, one library call.
     Returns (dF, dt) with dt = gamma * dL_r/dt."""

@@ -57,8 +57,12 @@ class MILinearBlock(nn.Module):
             w[torch.arange(k), torch.arange(k)] = 1.0
         self.bln = bln
 
+    def pre_norm(self, feat: torch.Tensor) -> torch.Tensor:
+        """The head's output before its LayerNorm (`f` of loss.py:36): what the fused tail kernels consume."""
+        return self.feature_nonlinear(feat) + self.feature_shortcut(feat)
+
     def forward(self, feat: torch.Tensor) -> torch.Tensor:
-        out = self.feature_nonlinear(feat) + self.feature_shortcut(feat)
+        out = self.pre_norm(feat)
         return self.feature_block_ln(out) if self.bln else out
 
 
@@ -108,8 +112,8 @@ class GlobalDiscriminatorDot(nn.Module):
         return (u * v).sum(-1) * self.temperature.exp()
 
 
-def _forward_block_twice(block: MILinearBlock, x: torch.Tensor) -> torch.Tensor:
-    """Run a projection head once while leaving its BatchNorm buffers exactly as the
+def _forward_block_twice(block: MILinearBlock, x: torch.Tensor, pre_norm: bool = False) -> torch.Tensor:
+    """Run a projection head once (pre_norm: up to, not including, its LayerNorm) while leaving its BatchNorm buffers exactly as the
     reference's two passes (positives, then the permuted negatives) leave them.  Both
     passes see the same batch statistics s, so the two updates r <- (1-m) r + m s
     collapse into one update with momentum m' = 1 - (1-m)^2 = m (2 - m); the buffers
@@ -118,8 +122,9 @@ def _forward_block_twice(block: MILinearBlock, x: torch.Tensor) -> torch.Tensor:
     bn = block.feature_nonlinear[1] if isinstance(block, MILinearBlock) else None
     replay = block.training and isinstance(bn, nn.BatchNorm1d) and bn.track_running_stats \
         and bn.running_mean is not None
+    run = block.pre_norm if pre_norm else block
     if not replay:
-        return block(x)
+        return run(x)
     momentum = bn.momentum
     if momentum is None:
         # cumulative average: factors 1/(n+1) then 1/(n+2) collapse into 2/(n+2)
@@ -127,7 +132,7 @@ def _forward_block_twice(block: MILinearBlock, x: torch.Tensor) -> torch.Tensor:
     else:
         bn.momentum = momentum * (2.0 - momentum)
     try:
-        out = block(x)
+        out = run(x)
     finally:
         bn.momentum = momentum
     with torch.no_grad():
@@ -163,6 +168,13 @@ class JSDInfoMaxLoss(nn.Module):
       grad_partials  exchange="peer", route="reduce": "bf16" (default; the partials travel as bf16
                 tiles pushed from the contraction's epilogue, measured 5-6e-3 of the 1e-2 gradient
                 tolerance) or "fp32" (exact to fp32, ~20 % more step time on 8 GPUs).
+      fused_heads  True: the LayerNorm that ends each projection head (loss.py:36-38) and the F.normalize that
+                follows it (loss.py:94-95) run as ONE row pass of libjsd_b200.so, forward and backward
+                (LayerNorm's weight / bias gradients included; its [B, D] output is never stored).  With
+                neg_mode="dense" on one GPU that pass IS the estimator's normalise / Jacobian pass (bf16 unit rows
+                and 1/||.|| straight from the pre-LayerNorm head output); in every other mode it hands fp32 unit
+                rows to the estimator.  Same values and gradients as the default (False: nn.LayerNorm + the
+                estimator's own normalisation), tested against the reference's golden vectors.
     """
 
     def __init__(
@@ -182,6 +194,7 @@ class JSDInfoMaxLoss(nn.Module):
         exchange: str = "nccl",
         route: str = "reduce",
         grad_partials: str = "bf16",
+        fused_heads: bool = False,
     ):
         super().__init__()
         if type not in _DOT_TYPES + _CONCAT_TYPES:
@@ -207,6 +220,7 @@ class JSDInfoMaxLoss(nn.Module):
         self.exchange = exchange
         self.route = route
         self.grad_partials = grad_partials
+        self.fused_heads = bool(fused_heads)
 
         self.global_d = (GlobalDiscriminatorDot(image_sz=image_dim, text_sz=text_dim) if type in _DOT_TYPES
                          else GlobalDiscriminator(sz=image_dim + text_dim))
@@ -247,9 +261,19 @@ class JSDInfoMaxLoss(nn.Module):
                   neg_index: Optional[ops.NegativeIndex], allow_dense: bool) -> torch.Tensor:
         """Em - Ej for one critic (the body shared by loss.py:204-254, :257-277, :280-300)."""
         if isinstance(critic, GlobalDiscriminatorDot):
-            f = _forward_block_twice(critic.img_block, feats1)
-            g = _forward_block_twice(critic.text_block, feats2)
-            if allow_dense and self.neg_mode == "dense":
+            dense = allow_dense and self.neg_mode == "dense"
+            if self.fused_heads and all(isinstance(blk, MILinearBlock) and blk.bln
+                                        for blk in (critic.img_block, critic.text_block)):
+                xf = _forward_block_twice(critic.img_block, feats1, pre_norm=True)
+                xg = _forward_block_twice(critic.text_block, feats2, pre_norm=True)
+                ln_f, ln_g = critic.img_block.feature_block_ln, critic.text_block.feature_block_ln
+                if dense and not self.gather:
+                    return ops.jsd_dense_loss_ln(xf, xg, ln_f, ln_g, critic.temperature)[0]
+                f, g = ops.ln_normalize_pair(xf, xg, ln_f, ln_g)
+            else:
+                f = _forward_block_twice(critic.img_block, feats1)
+                g = _forward_block_twice(critic.text_block, feats2)
+            if dense:
                 if self.gather and self.exchange == "peer":
                     from . import peer
                     loss, _ = peer.peer_dense_loss(f, g, critic.temperature, self.process_group, route=self.route,
@@ -272,6 +296,11 @@ class JSDInfoMaxLoss(nn.Module):
         em = F.softplus(critic(feats1, feats2_neg)).mean()
         return em - ej
 
+    @staticmethod
+    def _require_cuda(features: torch.Tensor) -> None:
+        if not features.is_cuda:
+            raise RuntimeError("JSDInfoMaxLoss (B200) needs CUDA tensors; there is no CPU path")
+
     # ------------------------------------------------------------------ forward
     def forward(
         self,
@@ -282,8 +311,7 @@ class JSDInfoMaxLoss(nn.Module):
         aug_image_features: Optional[torch.Tensor] = None,
         aug_text_features: Optional[torch.Tensor] = None,
     ) -> Dict[str, torch.Tensor]:
-        if not image_features.is_cuda:
-            raise RuntimeError("JSDInfoMaxLoss (B200) needs CUDA tensors; there is no CPU path")
+        self._require_cuda(image_features)
         if image_features.shape[0] != text_features.shape[0]:
             raise ValueError("image and text batches differ in size")
         device = image_features.device

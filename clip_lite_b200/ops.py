@@ -4,6 +4,8 @@ loss.py:94-105,204-254 and of its backward runs in libjsd_b200.so.
 
     jsd_index_loss(f, g, t, neg_index=None)   reference semantics: one indexed negative per row
     jsd_dense_loss(f, g, t)                   all off-diagonal pairs as negatives (single GPU)
+    ln_normalize_pair(xf, xg, ln_f, ln_g)     tail of the projection heads: LayerNorm + F.normalize in one pass
+    jsd_dense_loss_ln(xf, xg, ln_f, ln_g, t)  jsd_dense_loss on the heads' pre-LayerNorm outputs, tail fused in
 
 f, g are the projected features ([B, D]; fp32, bf16 or fp16), t the 0-dim
 `temperature` parameter.  Both return (loss, stats) where loss is the 0-dim
@@ -131,6 +133,125 @@ class _JSDDenseFn(torch.autograd.Function):
             df, dg, dt = fn(fc, gc, t, grad_loss, saved)
         fd, gd, td = ctx.dtypes
         return df.to(fd), dg.to(gd), dt.to(td)
+
+
+def _ln_args(ln):
+    """(weight, bias, eps) of an nn.LayerNorm (or of a plain tuple)."""
+    if isinstance(ln, torch.nn.LayerNorm):
+        return ln.weight, ln.bias, float(ln.eps)
+    w, b, eps = ln
+    return w, b, float(eps)
+
+
+def _pair_inputs(xf: torch.Tensor, xg: torch.Tensor):
+    if xf.dim() != 2 or xg.dim() != 2 or xf.shape != xg.shape:
+        raise ValueError(f"head outputs must be two [B, D] tensors of the same shape; got {tuple(xf.shape)} and "
+                         f"{tuple(xg.shape)}")
+    if not (xf.is_cuda and xg.is_cuda):
+        raise RuntimeError("the projection-head tail runs on CUDA only (no CPU fallback)")
+    dt = torch.promote_types(xf.dtype, xg.dtype)
+    if dt not in (torch.float32, torch.bfloat16, torch.float16):
+        dt = torch.float32
+    return xf.to(dt).contiguous(), xg.to(dt).contiguous()
+
+
+def _param_grad(g: Optional[torch.Tensor], p: Optional[torch.Tensor]):
+    return None if (g is None or p is None) else g.to(p.dtype)
+
+
+class _LnNormalizePairFn(torch.autograd.Function):
+    """(xf, xg) -> fp32 unit rows of LN(xf), LN(xg): one launch forward; backward = Jacobian of F.normalize +
+    LayerNorm backward + the weight / bias sums in one pass over (x, upstream gradient) and one small reduction
+    launch.  The [B, D] LayerNorm output is never stored: 12 bytes per row (mean, rstd, 1/||.||) are kept."""
+
+    @staticmethod
+    def forward(ctx, xf, xg, wf, bf, wg, bg, eps_f, eps_g):
+        with torch.autocast("cuda", enabled=False):
+            xfc, xgc = _pair_inputs(xf, xg)
+            uf, ug, st_f, st_g = K.ln_normalize_pair(xfc, xgc, (wf, bf, eps_f), (wg, bg, eps_g), out_bf16=False)
+        ctx.save_for_backward(xfc, xgc, wf, bf, wg, bg, st_f, st_g)
+        ctx.dtypes = (xf.dtype, xg.dtype)
+        return uf, ug
+
+    @staticmethod
+    def backward(ctx, guf, gug):
+        xfc, xgc, wf, bf, wg, bg, st_f, st_g = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            guf = torch.zeros_like(xfc, dtype=torch.float32) if guf is None else guf.float().contiguous()
+            gug = torch.zeros_like(xgc, dtype=torch.float32) if gug is None else gug.float().contiguous()
+            dxf, dxg, dwf, dbf, dwg, dbg, _ = K.ln_normalize_bwd_pair(xfc, xgc, (wf, bf, 0.0), (wg, bg, 0.0), st_f,
+                                                                      st_g, guf, gug)
+        fd, gd = ctx.dtypes
+        return (dxf.to(fd), dxg.to(gd), _param_grad(dwf, wf), _param_grad(dbf, bf), _param_grad(dwg, wg),
+                _param_grad(dbg, bg), None, None)
+
+
+def ln_normalize_pair(xf: torch.Tensor, xg: torch.Tensor, ln_f, ln_g):
+    """Tail of the two projection heads (reference loss.py:36-38 then :94-95) in one launch: fp32 unit rows
+    LN(x) / max(||LN(x)||, 1e-12) of the image and the text head.  ln_* is the head's nn.LayerNorm (or a
+    (weight, bias, eps) tuple).  Feed the result to jsd_index_loss / any gathered estimator: their own
+    normalisation of a unit row is the identity, and its Jacobian is the projection this backward applies anyway."""
+    wf, bf, ef = _ln_args(ln_f)
+    wg, bg, eg = _ln_args(ln_g)
+    return _LnNormalizePairFn.apply(xf, xg, wf, bf, wg, bg, ef, eg)
+
+
+class _JSDDenseLnFn(torch.autograd.Function):
+    """jsd_dense_loss with the heads' tail fused into its row passes (single GPU): the forward's normalise pass
+    applies LayerNorm first (bf16 unit rows straight from the pre-LayerNorm head output), the backward's Jacobian
+    pass continues through LayerNorm and sums its weight / bias gradients -- no LayerNorm output, no separate
+    LayerNorm kernels in either direction."""
+
+    @staticmethod
+    def forward(ctx, xf, xg, wf, bf, wg, bg, t, eps_f, eps_g):
+        need_grad = any(ctx.needs_input_grad)
+        with torch.autocast("cuda", enabled=False):
+            xfc, xgc = _pair_inputs(xf, xg)
+            b, d = xfc.shape
+            u, v, st_f, st_g = K.ln_normalize_pair(xfc, xgc, (wf, bf, eps_f), (wg, bg, eps_g), out_bf16=True)
+            ctx.fused = need_grad and K.fused_supported(b, d)
+            if ctx.fused:
+                out4, loss, gdiag, acc = K.dense_fused_fwd_bwd(u, v, t)
+                keep = (acc,)
+            else:
+                out4, loss, gmat, gdiag = K.dense_fwd(u, v, t, 0, want_grad=need_grad)
+                keep = (gmat,) if need_grad else ()
+        if need_grad:
+            ctx.save_for_backward(xfc, xgc, wf, bf, wg, bg, t, u, v, st_f, st_g, gdiag, *keep)
+        ctx.dtypes = (xf.dtype, xg.dtype, t.dtype)
+        ctx.mark_non_differentiable(out4)
+        return loss, out4
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        xfc, xgc, wf, bf, wg, bg, t, u, v, st_f, st_g, gdiag, kept = ctx.saved_tensors
+        b = xfc.shape[0]
+        with torch.autocast("cuda", enabled=False):
+            gamma = grad_loss.float()
+            if ctx.fused:
+                acc_u, acc_v, scale = kept[0], kept[1], 1.0 / (b * (b - 1.0))
+            else:
+                acc_u = K.dense_bwd_du(kept, v, t, gamma)
+                acc_v = K.dense_bwd_dv(kept, u, b, t, gamma)
+                scale = 0.0
+            dxf, dxg, dwf, dbf, dwg, dbg, dt = K.ln_normalize_bwd_pair(
+                xfc, xgc, (wf, bf, 0.0), (wg, bg, 0.0), st_f, st_g, acc_u, acc_v, acc_scale=scale, partner0=v,
+                partner1=u, gdiag=gdiag, t=t, gamma=gamma, m_rows=b, want_dt=True)
+        fd, gd, td = ctx.dtypes
+        return (dxf.to(fd), dxg.to(gd), _param_grad(dwf, wf), _param_grad(dbf, bf), _param_grad(dwg, wg),
+                _param_grad(dbg, bg), dt.to(td), None, None)
+
+
+def jsd_dense_loss_ln(xf: torch.Tensor, xg: torch.Tensor, ln_f, ln_g, t: torch.Tensor):
+    """All-pairs estimator on the projection heads' PRE-LayerNorm outputs (loss.py:36 `f` before
+    feature_block_ln): LayerNorm, F.normalize, the bf16 cast and 1/||.|| happen in the estimator's own row pass,
+    and so does their backward.  Same value and gradients as jsd_dense_loss(ln_f(xf), ln_g(xg), t), plus the
+    LayerNorm parameter gradients."""
+    if xf.shape[0] < 2:
+        raise ValueError("the dense estimator needs at least two rows (one negative per row)")
+    wf, bf, ef = _ln_args(ln_f)
+    wg, bg, eg = _ln_args(ln_g)
+    return _JSDDenseLnFn.apply(xf, xg, wf, bf, wg, bg, t, ef, eg)
 
 
 def jsd_index_loss(f: torch.Tensor, g: torch.Tensor, t: torch.Tensor, neg_index: Optional[NegativeIndex] = None):

@@ -190,6 +190,44 @@ int jsd_dense_backward_image_side(const void* F, int dtype, int64_t M, int64_t N
                                   float* rowdot, void* workspace, void* sk_workspace, void* dF, float* dt_out,
                                   jsd_stream_t stream);
 
+/* ------------------------------------------------------------------ projection-head tail (LayerNorm + normalise)
+ * replaces: the nn.LayerNorm that ends MILinearBlock.forward (loss.py:36-38) fused with the F.normalize of
+ *           GlobalDiscriminatorDot.forward (loss.py:94-95), forward and backward.
+ * X0 / X1   [rows, D] head outputs BEFORE LayerNorm (`dtype`): image head / text head; X1 (with out1, stats1, ...)
+ *           may be NULL = one row set only
+ * w, b      LayerNorm weight / bias, fp32 [D]; NULL = 1 / 0 (elementwise_affine=False).  eps = LayerNorm's eps.
+ *
+ * jsd_ln_normalize_pair      u = LN(x) / max(||LN(x)||, 1e-12), one pass over each row:
+ *     out_bf16 = 0: out fp32 [rows, D]  (input of jsd_index_fwd_bwd or of any other consumer of unit rows)
+ *     out_bf16 = 1: out bf16 [rows, D]  (the U / V operands of jsd_dense_fwd, jsd_dense_fused_fwd_bwd)
+ *     stats [3, rows] fp32: mean | rstd | 1 / max(||LN(x)||, 1e-12)  -- all the backward keeps of LayerNorm's output
+ * jsd_ln_normalize_bwd_pair  one pass: dU = acc_scale' * sum_s acc[s] + gamma tau / M_rows * gdiag[row] * partner[row
+ *     + partner_offset] (as jsd_normalize_bwd), Jacobian of F.normalize, LayerNorm backward:
+ *     acc       fp32 [n_slices][rows, D], slices `slice_stride` elements apart, summed in order.  The gradient with
+ *               respect to the unit rows (index mode: dF / dG of jsd_index_fwd_bwd on the unit rows), the scaled
+ *               accumulators of jsd_dense_bwd_du / _dv (acc_scale = 0: taken as they are), or the unscaled slices
+ *               of jsd_dense_fused_fwd_bwd (acc_scale = 1 / (B (B - 1)): multiplied by gamma * tau * acc_scale)
+ *     gdiag     NULL = no positive-pair term (partner, t_dev, M_rows unused unless acc_scale > 0 needs t_dev)
+ *     dX        [rows, D] in `dtype`: gradient of the head output;  dw, db fp32 [D] (may be NULL): LayerNorm's
+ *               weight / bias gradients, summed over the rows per block in registers and over the blocks in a
+ *               fixed order by a second small launch (deterministic, no atomics)
+ *     rowdot    optional [rows]: <u_row, dU_row> of row set 0; dt_out (optional, needs rowdot) = their sum
+ *               = gamma * dL/dt of the dense estimator
+ *     workspace >= jsd_ln_workspace_bytes(rows, D) bytes (per-block column partials; no initialisation needed)
+ * D <= 4096 when rows are 16-byte aligned and D % 4 == 0, else D <= 1024 (the heads' width is 2048). */
+size_t jsd_ln_workspace_bytes(int64_t rows, int64_t D);
+int jsd_ln_normalize_pair(const void* X0, const void* X1, int dtype, int64_t rows, int64_t D, const float* w0,
+                          const float* b0, float eps0, const float* w1, const float* b1, float eps1, int out_bf16,
+                          void* out0, void* out1, float* stats0, float* stats1, jsd_stream_t stream);
+int jsd_ln_normalize_bwd_pair(const void* X0, const void* X1, int dtype, int64_t rows, int64_t D, const float* w0,
+                              const float* b0, const float* w1, const float* b1, const float* stats0,
+                              const float* stats1, const float* acc0, const float* acc1, int64_t n_slices,
+                              int64_t slice_stride, float acc_scale, const void* partner0_bf16,
+                              int64_t partner_offset0, const void* partner1_bf16, int64_t partner_offset1,
+                              const float* gdiag, const float* t_dev, const float* gamma_dev, int64_t M_rows,
+                              void* workspace, void* dX0, void* dX1, float* dw0, float* db0, float* dw1, float* db1,
+                              float* rowdot, float* dt_out, jsd_stream_t stream);
+
 /* ------------------------------------------------------------------ peer-memory exchange (multi-GPU dense path)
  * One process per GPU; the two exchange steps of the sharded path (all-gather of the text rows, sum of
  * the dV partials on the owner rank) are fused into the kernels that produce / consume the data, over NVLink peer

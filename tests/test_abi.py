@@ -130,3 +130,29 @@ def test_integration_stub_matches_the_binding():
     calls = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute)
              and n.func.attr == "jsd_index_fwd_bwd"]
     assert calls and all(len(c.args) == len(_lib.SIGNATURES["jsd_index_fwd_bwd"][1]) for c in calls)
+
+
+def test_gpu_verified_kernels_are_unchanged():
+    """Every kernel of the build that last ran green on a B200 (profiles/sass_manifest_gpu_verified_r02.txt: one md5
+    of the disassembly per kernel) is byte-identical in the current build: kernels added since then (the
+    projection-head tail, written without a GPU at hand) did not touch the verified machine code.  After a GPU run
+    of a deliberate kernel change, regenerate the manifest with tools/sass_diff.py --manifest."""
+    import shutil
+    import subprocess
+    import sys
+    from clip_lite_b200 import build
+    manifest = os.path.join(ROOT, "profiles", "sass_manifest_gpu_verified_r02.txt")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not (shutil.which("cuobjdump") and os.path.exists(nvcc)):
+        pytest.skip("CUDA toolkit not available")
+    if "V12.9.86" not in subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout:
+        pytest.skip("manifest was written by nvcc 12.9.86")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import sass_diff
+    finally:
+        sys.path.pop(0)
+    changed, added, removed = sass_diff.compare(sass_diff.read_manifest(manifest),
+                                                sass_diff.kernels(build.build_library()))
+    assert not changed and not removed, (changed, removed)
+    assert all("ln_normalize" in k or "ln_bwd_finalize" in k for k in added), added

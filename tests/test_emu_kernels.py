@@ -312,3 +312,46 @@ def test_ln_backward_plan_rejects_oversized_rows(emu):
                                        1, 0, 0.0, None, 0, None, 0, None, None, None, rows, ptr(ws), ptr(dx), None,
                                        None, None, None, None, None, None, 1, 0)
     assert rc == -1
+
+
+# ------------------------------------------------------------------ racecheck on the CPU
+def test_head_tail_kernels_are_race_free_under_tsan(tmp_path):
+    """compute-sanitizer --tool racecheck needs a GPU; here the same question is put to ThreadSanitizer: with one OS
+    thread per CUDA thread and barriers as the only synchronisation, any shared- or global-memory access of the
+    LayerNorm / normalise kernels that a __syncthreads / __syncwarp does not order is a data race TSan reports.
+    A deliberately broken block reduction (--racy) is the negative control: the check only counts where it fires."""
+    import os
+    import subprocess
+    exe = str(tmp_path / "racecheck")
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-Wno-tsan", "-DJSD_HOST_EMU",
+           "-I" + _emu_backend.CUDA_INC, "-I" + _emu_backend.EMU_DIR, "-I" + _emu_backend.CSRC,
+           os.path.join(_emu_backend.EMU_DIR, "emu_racecheck.cpp"), "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("ThreadSanitizer build not available: " + res.stderr[-300:])
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    racy = subprocess.run([exe, "--racy"], capture_output=True, text=True, env=env, timeout=300)
+    if racy.returncode != 66:
+        pytest.skip("ThreadSanitizer is not functional in this environment (the negative control did not fire)")
+    assert "data race" in racy.stderr
+    ok = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=600)
+    assert ok.returncode == 0, ok.stderr[-3000:]
+    assert "racecheck cases done rc=0" in ok.stdout
+
+
+def test_head_tail_kernels_are_memcheck_clean_under_asan(tmp_path):
+    """The CPU stand-in for compute-sanitizer --tool memcheck: the same cases with exactly-sized heap buffers under
+    AddressSanitizer + UBSan (an access one element past a row, a partial buffer or the workspace aborts)."""
+    import os
+    import subprocess
+    exe = str(tmp_path / "memcheck")
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+           "-DJSD_HOST_EMU", "-I" + _emu_backend.CUDA_INC, "-I" + _emu_backend.EMU_DIR, "-I" + _emu_backend.CSRC,
+           os.path.join(_emu_backend.EMU_DIR, "emu_racecheck.cpp"), "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        pytest.skip("AddressSanitizer build not available: " + res.stderr[-300:])
+    ok = subprocess.run([exe], capture_output=True, text=True, timeout=600,
+                        env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert ok.returncode == 0, (ok.stdout[-500:], ok.stderr[-3000:])
+    assert "racecheck cases done rc=0" in ok.stdout

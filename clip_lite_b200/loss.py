@@ -112,9 +112,11 @@ class GlobalDiscriminatorDot(nn.Module):
         return (u * v).sum(-1) * self.temperature.exp()
 
 
-def _forward_block_twice(block: MILinearBlock, x: torch.Tensor, pre_norm: bool = False) -> torch.Tensor:
-    """Run a projection head once (pre_norm: up to, not including, its LayerNorm) while leaving its BatchNorm buffers exactly as the
-    reference's two passes (positives, then the permuted negatives) leave them.  Both
+def _forward_block_twice(block: MILinearBlock, x: torch.Tensor, pre_norm: bool = False,
+                         dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Run a projection head once (pre_norm: up to, not including, its LayerNorm; dtype: under
+    torch.autocast(dtype), i.e. its GEMMs as reduced-precision tensor-core library calls) while leaving its
+    BatchNorm buffers exactly as the reference's two passes (positives, then the permuted negatives) leave them.  Both
     passes see the same batch statistics s, so the two updates r <- (1-m) r + m s
     collapse into one update with momentum m' = 1 - (1-m)^2 = m (2 - m); the buffers
     are therefore only ever written by BatchNorm itself (never in place behind
@@ -122,7 +124,13 @@ def _forward_block_twice(block: MILinearBlock, x: torch.Tensor, pre_norm: bool =
     bn = block.feature_nonlinear[1] if isinstance(block, MILinearBlock) else None
     replay = block.training and isinstance(bn, nn.BatchNorm1d) and bn.track_running_stats \
         and bn.running_mean is not None
-    run = block.pre_norm if pre_norm else block
+    head = block.pre_norm if pre_norm else block
+    if dtype is None:
+        run = head
+    else:
+        def run(inp):
+            with torch.autocast(device_type=inp.device.type, dtype=dtype):
+                return head(inp)
     if not replay:
         return run(x)
     momentum = bn.momentum
@@ -175,6 +183,12 @@ class JSDInfoMaxLoss(nn.Module):
                 and 1/||.|| straight from the pre-LayerNorm head output); in every other mode it hands fp32 unit
                 rows to the estimator.  Same values and gradients as the default (False: nn.LayerNorm + the
                 estimator's own normalisation), tested against the reference's golden vectors.
+      heads_dtype  None (default): the projection heads run in whatever precision the caller's context gives them
+                (fp32, or fp16 under the reference's amp.autocast, train.py:214).  torch.bfloat16 / torch.float16:
+                the heads' five GEMMs run under torch.autocast(dtype) as tensor-core library GEMMs whatever the
+                caller's context is -- the GradScaler-free bf16 route.  A precision choice of
+                the caller: features then carry bf16 rounding (~3 significant digits), the estimator itself still
+                accumulates in fp32.
     """
 
     def __init__(
@@ -195,6 +209,7 @@ class JSDInfoMaxLoss(nn.Module):
         route: str = "reduce",
         grad_partials: str = "bf16",
         fused_heads: bool = False,
+        heads_dtype: Optional[torch.dtype] = None,
     ):
         super().__init__()
         if type not in _DOT_TYPES + _CONCAT_TYPES:
@@ -221,6 +236,9 @@ class JSDInfoMaxLoss(nn.Module):
         self.route = route
         self.grad_partials = grad_partials
         self.fused_heads = bool(fused_heads)
+        if heads_dtype not in (None, torch.bfloat16, torch.float16):
+            raise ValueError(f"heads_dtype must be None, torch.bfloat16 or torch.float16, got {heads_dtype!r}")
+        self.heads_dtype = heads_dtype
 
         self.global_d = (GlobalDiscriminatorDot(image_sz=image_dim, text_sz=text_dim) if type in _DOT_TYPES
                          else GlobalDiscriminator(sz=image_dim + text_dim))
@@ -264,15 +282,15 @@ class JSDInfoMaxLoss(nn.Module):
             dense = allow_dense and self.neg_mode == "dense"
             if self.fused_heads and all(isinstance(blk, MILinearBlock) and blk.bln
                                         for blk in (critic.img_block, critic.text_block)):
-                xf = _forward_block_twice(critic.img_block, feats1, pre_norm=True)
-                xg = _forward_block_twice(critic.text_block, feats2, pre_norm=True)
+                xf = _forward_block_twice(critic.img_block, feats1, pre_norm=True, dtype=self.heads_dtype)
+                xg = _forward_block_twice(critic.text_block, feats2, pre_norm=True, dtype=self.heads_dtype)
                 ln_f, ln_g = critic.img_block.feature_block_ln, critic.text_block.feature_block_ln
                 if dense and not self.gather:
                     return ops.jsd_dense_loss_ln(xf, xg, ln_f, ln_g, critic.temperature)[0]
                 f, g = ops.ln_normalize_pair(xf, xg, ln_f, ln_g)
             else:
-                f = _forward_block_twice(critic.img_block, feats1)
-                g = _forward_block_twice(critic.text_block, feats2)
+                f = _forward_block_twice(critic.img_block, feats1, dtype=self.heads_dtype)
+                g = _forward_block_twice(critic.text_block, feats2, dtype=self.heads_dtype)
             if dense:
                 if self.gather and self.exchange == "peer":
                     from . import peer

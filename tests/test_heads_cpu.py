@@ -4,7 +4,7 @@ CPU emulation of the same kernel source (tests/_emu_backend.py), the tensor-core
 stand-ins.  Checks the ctypes marshalling of the long argument lists, the autograd wiring (which gradient goes to
 which input, LayerNorm parameters included) and the module option -- against fp64 PyTorch autograd of
 LayerNorm -> estimator and against the golden vectors generated from the unmodified reference module.
-The GPU tier (tests/test_gpu_heads.py) repeats the same comparisons on the real library."""
+The GPU tier (tests/test_zz_gpu_heads.py) repeats the same comparisons on the real library."""
 import os
 
 import numpy as np
@@ -222,3 +222,43 @@ def test_fused_heads_skips_blocks_without_layernorm(monkeypatch):
     m.global_d.text_block = torch.nn.Identity()
     out = m(torch.randn(6, 16), torch.randn(6, 16))
     assert torch.isfinite(out["total_loss"]) and calls == ["jsd_index_fwd_bwd"]
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_heads_dtype_runs_the_heads_under_autocast(monkeypatch, fused):
+    """heads_dtype=torch.bfloat16: the heads' GEMMs run under torch.autocast(bf16) whatever the caller's context is
+    (the tail / estimator then read bf16 head outputs); the result stays within bf16 rounding of the fp32 module and
+    the BatchNorm double-update replay is unaffected."""
+    from clip_lite_b200 import loss as L
+    _emu_backend.install(monkeypatch)
+    monkeypatch.setattr(L.JSDInfoMaxLoss, "_require_cuda", staticmethod(lambda t: None))
+    seen = []
+    orig = L.MILinearBlock.pre_norm
+
+    def spy(self, feat):
+        out = orig(self, feat)
+        seen.append(out.dtype)
+        return out
+
+    monkeypatch.setattr(L.MILinearBlock, "pre_norm", spy)
+    img, txt = torch.randn(16, 24), torch.randn(16, 20)
+
+    def run(dtype):
+        torch.manual_seed(0)
+        m = L.JSDInfoMaxLoss(image_dim=24, text_dim=20, image_prior=False, fused_heads=fused, heads_dtype=dtype)
+        a, b = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        out = m(a, b)
+        out["total_loss"].backward()
+        return m, out, a.grad
+
+    m16, o16, g16 = run(torch.bfloat16)
+    assert seen and all(d == torch.bfloat16 for d in seen)
+    seen.clear()
+    m32, o32, g32 = run(None)
+    assert all(d == torch.float32 for d in seen)
+    assert abs(float(o16["total_loss"]) - float(o32["total_loss"])) < 3e-2 * abs(float(o32["total_loss"]))
+    assert g16.dtype == torch.float32 and rel(g16, g32) < 0.15
+    bn16, bn32 = m16.global_d.img_block.feature_nonlinear[1], m32.global_d.img_block.feature_nonlinear[1]
+    assert int(bn16.num_batches_tracked) == int(bn32.num_batches_tracked) == 2
+    assert rel(bn16.running_mean, bn32.running_mean) < 3e-2
+    assert all(p.grad is None or p.grad.dtype == p.dtype for p in m16.parameters())

@@ -68,7 +68,10 @@ def test_bad_options_raise():
         L.JSDInfoMaxLoss(image_dim=8, text_dim=8, neg_mode="dense", gather=True, route="ring")
     m = L.JSDInfoMaxLoss(image_dim=8, text_dim=8, neg_mode="dense", gather=True, exchange="peer", route="symmetric")
     assert (m.exchange, m.route) == ("peer", "symmetric")
+    with pytest.raises(ValueError):
+        L.JSDInfoMaxLoss(image_dim=8, text_dim=8, heads_dtype=torch.float64)
     d = L.JSDInfoMaxLoss(image_dim=8, text_dim=8)
+    assert (d.fused_heads, d.heads_dtype) == (False, None)               # reference behaviour unless asked otherwise
     assert (d.exchange, d.route) == ("nccl", "reduce")                  # collectives + reduce unless asked otherwise
 
 

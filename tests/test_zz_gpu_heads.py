@@ -326,3 +326,24 @@ def test_module_fused_heads_under_autocast_and_grad_scaler(L):
     ln = m.global_d.img_block.feature_block_ln
     assert ln.weight.grad is not None and torch.isfinite(ln.weight.grad).all() and float(ln.weight.grad.abs().max()) > 0
     assert all(p.grad is None or p.grad.dtype == p.dtype for p in m.parameters())
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_heads_dtype_bf16(L, fused):
+    """heads_dtype=torch.bfloat16 (no outer autocast, no GradScaler): the heads' GEMMs run as bf16 library GEMMs,
+    the tail / estimator read their bf16 output; losses stay within bf16 rounding of the fp32 module."""
+    def run(dtype):
+        torch.manual_seed(0)
+        m = L.JSDInfoMaxLoss(image_dim=64, text_dim=48, image_prior=False, fused_heads=fused, heads_dtype=dtype).cuda()
+        g = torch.Generator(device="cuda").manual_seed(1)
+        img = torch.randn(64, 64, device="cuda", generator=g).requires_grad_(True)
+        txt = torch.randn(64, 48, device="cuda", generator=g).requires_grad_(True)
+        out = m(img, txt)
+        out["total_loss"].backward()
+        return m, out, img.grad
+
+    m16, o16, g16 = run(torch.bfloat16)
+    m32, o32, g32 = run(None)
+    assert abs(float(o16["total_loss"]) - float(o32["total_loss"])) < 3e-2 * abs(float(o32["total_loss"]))
+    assert g16.dtype == torch.float32 and torch.isfinite(g16).all() and relerr(g16, g32) < 0.2
+    assert all(p.grad is None or (p.grad.dtype == p.dtype and torch.isfinite(p.grad).all()) for p in m16.parameters())

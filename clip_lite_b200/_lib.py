@@ -145,7 +145,22 @@ def check(rc: int, what: str) -> None:
         raise JSDLibraryError(f"{what} failed: {msg}")
 
 
+# JSD_NVTX=1: every library call is wrapped in an NVTX range named after the entry point, so that the ranges an
+# `ncu --nvtx --nvtx-include "jsd_dense_forward/"` capture (or any NVTX-aware profiler) selects are the library's own
+# call boundaries (the reference has no NVTX either).  Off by default: two extra host calls per FFI
+# crossing are measurable on the latency-bound configs[1] steps when they run eagerly.
+NVTX = os.environ.get("JSD_NVTX", "0") == "1"
+
+
 def call(name: str, *args) -> None:
-    rc = getattr(_lib or load(), name)(*args)
+    if NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(_lib or load(), name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        rc = getattr(_lib or load(), name)(*args)
     if rc != 0:
         check(rc, name)

@@ -3,8 +3,9 @@
 nsys is not available on the GPU boxes and ncu serialises launches, which hides exactly what matters for the
 peer-exchange path: when each kernel of a graph replay starts, how long it waits for its peers' flags, when it
 ends.  The trace code is compiled in only into the instrumented build: ``build.build_library(trace=True)`` writes
-``csrc/libjsd_b200_trace.so``; run with ``JSD_LIB=<that path>``.  (Written at the end of round 1 without GPU time
-left to exercise it: treat it as untested until its first run.)  ``with KernelTrace() as tr: ...; tr.events()`` installs a buffer into which one thread of every kernel
+``csrc/libjsd_b200_trace.so``; run with ``JSD_LIB=<that path>`` (first used in round 2: the nine peer-exchange
+timelines under ``profiles/trace_peer_*`` come from it, via ``tools/trace_peer.py``).
+``with KernelTrace() as tr: ...; tr.events()`` installs a buffer into which one thread of every kernel
 stamps ``%globaltimer``; works inside CUDA-graph replays (enable it BEFORE capturing or replaying, not during a
 capture) and on every rank of a multi-GPU run (each rank traces its own device; the timers of different GPUs are
 only loosely aligned, so compare intervals, not absolute times, across ranks).

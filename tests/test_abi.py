@@ -156,3 +156,16 @@ def test_gpu_verified_kernels_are_unchanged():
                                                 sass_diff.kernels(build.build_library()))
     assert not changed and not removed, (changed, removed)
     assert all("ln_normalize" in k or "ln_bwd_finalize" in k for k in added), added
+
+
+def test_nvtx_ranges_wrap_library_calls(monkeypatch):
+    """JSD_NVTX=1: one NVTX range per entry point, popped even when the call fails."""
+    import torch
+    from clip_lite_b200 import _lib
+    events = []
+    monkeypatch.setattr(_lib, "NVTX", True)
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda name: events.append(("push", name)))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: events.append(("pop",)))
+    with pytest.raises(_lib.JSDLibraryError):
+        _lib.call("jsd_dense_fwd", None, None, 8, 8, 8, 0, None, None, 0, None, None, None, None, None)
+    assert events == [("push", "jsd_dense_fwd"), ("pop",)]

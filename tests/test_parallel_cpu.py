@@ -228,3 +228,78 @@ def test_peer_autograd_wiring_matches_single_process_dense(world, route):
         _, pushes, steps = results[r]
         assert pushes == ((1, 1) if route == "symmetric" else (1, 0))
         assert steps == 3                       # the exchange's step counter advanced once per forward
+
+
+# ------------------------------------------------------------------ fused head tail in front of the gathered estimator
+def _fused_tail_worker(rank, world, port, results):
+    from tests import _emu_backend, _standin_kernels
+    from clip_lite_b200 import ops, parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mp_ = pytest.MonkeyPatch()
+    try:
+        _emu_backend.install(mp_)                  # row-wise entry points -> CPU emulation of the kernel source
+        parallel.K = _standin_kernels
+        xf, xg, lns = _tail_inputs()
+        m = B // world
+        xfl = xf[rank * m:(rank + 1) * m].clone().requires_grad_(True)
+        xgl = xg[rank * m:(rank + 1) * m].clone().requires_grad_(True)
+        t = torch.tensor(T, requires_grad=True)
+        f, g = ops.ln_normalize_pair(xfl, xgl, lns[0], lns[1])
+        loss, _ = parallel.gathered_dense_loss(f, g, t)
+        (0.5 * loss).backward()
+        results[rank] = (loss.detach(), xfl.grad, xgl.grad, t.grad,
+                         [p.grad.clone() for ln in lns for p in (ln.weight, ln.bias)])
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def _tail_inputs():
+    gen = torch.Generator().manual_seed(5)
+    xf = torch.randn(B, D, generator=gen) * 1.5 + 0.2
+    xg = 0.5 * xf + torch.randn(B, D, generator=gen)
+    lns = []
+    for _ in range(2):
+        ln = torch.nn.LayerNorm(D)
+        with torch.no_grad():
+            ln.weight.copy_(1.0 + 0.3 * torch.randn(D, generator=gen))
+            ln.bias.copy_(0.2 * torch.randn(D, generator=gen))
+        lns.append(ln)
+    return xf, xg, lns
+
+
+def test_fused_head_tail_in_front_of_the_gathered_loss():
+    """fused_heads=True with gather=True: every rank runs the LayerNorm + normalise tail on its own rows and hands
+    fp32 unit rows to the gathered estimator.  LayerNorm is row-wise, so the sharded run must reproduce the
+    single-process gradients of LayerNorm -> dense estimator on the whole batch: input gradients x world (DDP's
+    mean convention), LayerNorm parameter gradients summing over the ranks to world x the global gradient."""
+    from tests import _emu_backend
+    if not _emu_backend.available():
+        pytest.skip("needs g++ and the CUDA headers")
+    _emu_backend.build()                           # once, before the ranks race for it
+    world = 2
+    results = mp.Manager().dict()
+    mp.spawn(_fused_tail_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    xf, xg, lns = _tail_inputs()
+    leaves = [xf.double().requires_grad_(True), xg.double().requires_grad_(True)]
+    params = [p.detach().double().requires_grad_(True) for ln in lns for p in (ln.weight, ln.bias)]
+    tt = torch.tensor(T, dtype=torch.float64, requires_grad=True)
+    f = torch.nn.functional.layer_norm(leaves[0], (D,), params[0], params[1], lns[0].eps)
+    g = torch.nn.functional.layer_norm(leaves[1], (D,), params[2], params[3], lns[1].eps)
+    (0.5 * orc.jsd_dense(f, g, tt)["loss"]).backward()
+    m = B // world
+    psum = [torch.zeros_like(p) for p in params]
+    tot_dt = 0.0
+    for r in range(world):
+        loss, gxf, gxg, gt, gp = results[r]
+        for got, leaf in ((gxf, leaves[0]), (gxg, leaves[1])):
+            ref = world * leaf.grad[r * m:(r + 1) * m]
+            assert (got.double() - ref).abs().max() < 1e-2 * ref.abs().max()
+        for acc, p in zip(psum, gp):
+            acc += p.double()
+        tot_dt += float(gt)
+    for acc, p in zip(psum, params):
+        assert (acc / world - p.grad).abs().max() < 1e-2 * p.grad.abs().max()
+    assert abs(tot_dt / world - float(tt.grad)) < 1e-2 * abs(float(tt.grad))

@@ -4,7 +4,7 @@ CUDA stream are handed to libjsd_b200.so.  Nothing here computes anything in
 PyTorch -- allocation and plumbing only."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -126,11 +126,47 @@ def synthetic_batch(batch: int, device, seed: int = 0, image_px: int = 224, toke
             "attention_mask": torch.ones(batch, tokens, dtype=torch.long).to(device)}
 
 
+REFERENCE_ROOT = os.environ.get("CLIPLITE_REFERENCE_ROOT", "/root/reference")
+
+
+def load_reference_loss_module():
+    """The UNMODIFIED reference loss.py, imported from where it lies (build container only; loss.py:9 does
+    `from utils import *`, which must resolve to the reference's own empty utils package)."""
+    import importlib.util
+    path = os.path.join(REFERENCE_ROOT, "loss.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"{path} not found: --loss reference runs where the reference tree is present")
+    had_utils = sys.modules.pop("utils", None)
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        spec = importlib.util.spec_from_file_location("cliplite_reference_loss_e2e", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        sys.modules.pop("utils", None)
+        if had_utils is not None:
+            sys.modules["utils"] = had_utils
+    return mod
+
+
+class cuda_calls_as_identity:
+    """loss.py:186,257,280 hard-code `.cuda()`: on a host without a GPU make Tensor.cuda the identity while the
+    reference runs (its files are never edited)."""
+
+    def __enter__(self):
+        self.orig = torch.Tensor.cuda
+        if not torch.cuda.is_available():
+            torch.Tensor.cuda = lambda t, *a, **k: t
+
+    def __exit__(self, *a):
+        torch.Tensor.cuda = self.orig
+
+
 def make_loss(kind: str, **kw):
-    """kind "reference": the unmodified /root/reference/loss.py (build container only); "b200": the drop-in."""
+    """kind "reference": the unmodified reference loss.py (build container only); "b200": the drop-in."""
     if kind == "reference":
-        from oracle import reference_loader as rl          # test / baseline infrastructure, never the product path
-        return rl.load_reference_loss().JSDInfoMaxLoss(**kw)
+        return load_reference_loss_module().JSDInfoMaxLoss(**kw)
     from clip_lite_b200.loss import JSDInfoMaxLoss
     return JSDInfoMaxLoss(**kw)
 
@@ -155,12 +191,8 @@ def main():
         if args.device == "cuda":
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     device = torch.device(args.device, torch.cuda.current_device()) if args.device == "cuda" else torch.device("cpu")
-    if args.loss == "reference" and device.type != "cuda":
-        from oracle import reference_loader as rl
-        ctx = rl.cuda_calls_neutralised()                  # loss.py:186,257,280 hard-code .cuda()
-    else:
-        import contextlib
-        ctx = contextlib.nullcontext()
+    import contextlib
+    ctx = cuda_calls_as_identity() if args.loss == "reference" else contextlib.nullcontext()
     torch.manual_seed(0)
     extra = {} if args.loss == "reference" else {"neg_mode": args.neg_mode, "fused_heads": args.fused_heads}
     loss = make_loss(args.loss, image_dim=2048, text_dim=768, type="dot", image_prior=True, text_prior=True, **extra)

@@ -169,3 +169,27 @@ def test_nvtx_ranges_wrap_library_calls(monkeypatch):
     with pytest.raises(_lib.JSDLibraryError):
         _lib.call("jsd_dense_fwd", None, None, 8, 8, 8, 0, None, None, 0, None, None, None, None, None)
     assert events == [("push", "jsd_dense_fwd"), ("pop",)]
+
+
+def test_head_tail_entry_points_validate_before_launching(lib):
+    """Argument checks of the projection-head tail run before any CUDA call (so they can be exercised without a GPU):
+    null pointers, incomplete second row set, oversized D, workspace size."""
+    fake = 0x1000                                             # never dereferenced: every case fails validation first
+    rc = lib.jsd_ln_normalize_pair(None, None, 0, 8, 64, None, None, 1e-5, None, None, 1e-5, 0, None, None, None, None,
+                                   None)
+    assert rc != 0 and b"null pointer" in lib.jsd_last_error()
+    rc = lib.jsd_ln_normalize_pair(fake, fake, 0, 8, 64, None, None, 1e-5, None, None, 1e-5, 0, fake, None, fake, None,
+                                   None)
+    assert rc != 0 and b"together" in lib.jsd_last_error()
+    args = [fake, None, 0, 4, 4104, None, None, None, None, fake, None, fake, None, 1, 0, 0.0, None, 0, None, 0, None,
+            None, None, 4, fake, fake, None, None, None, None, None, None, None, None]
+    rc = lib.jsd_ln_normalize_bwd_pair(*args)
+    assert rc != 0 and b"too large" in lib.jsd_last_error()
+    args[13] = 0                                              # n_slices = 0
+    rc = lib.jsd_ln_normalize_bwd_pair(*args)
+    assert rc != 0 and b"slices" in lib.jsd_last_error()
+    args[13], args[20] = 1, fake                              # gdiag without partner rows / temperature
+    rc = lib.jsd_ln_normalize_bwd_pair(*args)
+    assert rc != 0 and b"positive-pair" in lib.jsd_last_error()
+    assert lib.jsd_ln_workspace_bytes(4, 64) == 2 * 4 * 2 * 64 * 4          # never more blocks than rows
+    assert lib.jsd_ln_workspace_bytes(0, 64) == 0

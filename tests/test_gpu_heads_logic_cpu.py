@@ -19,7 +19,20 @@ GEN = os.path.join(HERE, "_generated_heads_as_cpu.py")
 SHRINK = {"(8192, 2048)": "(16, 2048)", "(1000, 2048)": "(10, 2048)", "(300, 1024)": "(9, 1024)",
           "(1024, 2048, 1, False)": "(12, 2048, 1, False)", "(128, 2048, 2, True)": "(8, 2048, 2, True)",
           "(200, 256, 3, True)": "(20, 256, 3, True)", "(512, 2048)": "(16, 2048)", "(1024, 2048)]": "(24, 2048)]",
-          "(512, 1024)": "(16, 1024)", "(1000, 256)": "(40, 256)", "(256, 128)": "(32, 128)"}
+          "(512, 1024)": "(16, 1024)", "(1000, 256)": "(40, 256)", "(256, 128)": "(32, 128)",
+          '("dense", 512, 128)': '("dense", 32, 128)', '("dense", 256, 2048)': '("dense", 16, 2048)',
+          '("index", 512, 2048)': '("index", 16, 2048)'}
+
+# CUDA graphs do not exist on the CPU: the rewrite replays the eager step through the same interface
+EAGER_GRAPHED_STEP = '''    class GraphedStep:
+        def __init__(self, loss_fn, f, g, t):
+            self.fn, self.t = loss_fn, t
+
+        def __call__(self, f, g):
+            f, g = f.clone().requires_grad_(True), g.clone().requires_grad_(True)
+            loss = self.fn(f, g, self.t)[0]
+            return (loss,) + tuple(torch.autograd.grad(loss, (f, g, self.t)))
+'''
 
 PREAMBLE = '''pytestmark = []
 from tests import _emu_backend
@@ -40,6 +53,9 @@ def test_gpu_head_tests_pass_on_the_cpu_emulation():
     assert marker in s
     s = s.replace(".cuda()", "").replace('torch.Generator(device="cuda")', "torch.Generator()")
     s = s.replace('device="cuda"', 'device="cpu"').replace(marker, PREAMBLE)
+    graph_import = "    from clip_lite_b200.graph import GraphedStep\n"
+    assert graph_import in s
+    s = s.replace(graph_import, EAGER_GRAPHED_STEP)
     for big, small in SHRINK.items():
         assert big in s, f"{big} no longer appears in test_zz_gpu_heads.py: update SHRINK"
         s = s.replace(big, small)

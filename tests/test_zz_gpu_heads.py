@@ -347,3 +347,27 @@ def test_heads_dtype_bf16(L, fused):
     assert abs(float(o16["total_loss"]) - float(o32["total_loss"])) < 3e-2 * abs(float(o32["total_loss"]))
     assert g16.dtype == torch.float32 and torch.isfinite(g16).all() and relerr(g16, g32) < 0.2
     assert all(p.grad is None or (p.grad.dtype == p.dtype and torch.isfinite(p.grad).all()) for p in m16.parameters())
+
+
+@pytest.mark.parametrize("mode,b,d", [("dense", 512, 128), ("dense", 256, 2048), ("index", 512, 2048)])
+def test_fused_tail_step_cuda_graph_replay_matches_eager(ops, mode, b, d):
+    """The fused-tail step is graph-capturable (no host sync, no allocation outside the graph's pool, the occupancy
+    query is not a stream operation) and a replay is bit-identical to the eager step on the same inputs."""
+    from clip_lite_b200.graph import GraphedStep
+    xf, xg, ln_f, ln_g = make_heads(b, d, seed=7)
+    t = torch.tensor(orc.T_INIT, device="cuda", requires_grad=True)
+
+    def loss_fn(a, c, tt):
+        if mode == "dense":
+            return ops.jsd_dense_loss_ln(a, c, ln_f, ln_g, tt)
+        f, g = ops.ln_normalize_pair(a, c, ln_f, ln_g)
+        return ops.jsd_index_loss(f, g, tt)
+
+    gs = GraphedStep(loss_fn, xf, xg, t)
+    for seed in (7, 8):
+        x2, y2, _, _ = make_heads(b, d, seed=seed)
+        loss, df, dg, dt = gs(x2, y2)
+        xl, yl = x2.clone().requires_grad_(True), y2.clone().requires_grad_(True)
+        ref_loss = loss_fn(xl, yl, t)[0]
+        rdf, rdg, rdt = torch.autograd.grad(ref_loss, (xl, yl, t))
+        assert torch.equal(loss, ref_loss) and torch.equal(df, rdf) and torch.equal(dg, rdg) and torch.equal(dt, rdt)

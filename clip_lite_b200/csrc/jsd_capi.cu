@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "jsd_dense.cuh"
 #include "jsd_fused.cuh"
@@ -1494,10 +1495,24 @@ int ln_bwd_block_cap(int64_t rows) {
 }
 template <typename Kernel>
 int ln_bwd_blocks(Kernel kernel, int threads, int64_t rows) {
+  // resident blocks per SM, asked once per (kernel, block size): the eager warm-up step every CUDA-graph capture
+  // needs fills the table, so a capture makes no runtime query
+  struct Entry { const void* fn; int threads, per_sm; };
+  static Entry table[32];
+  static int used = 0;
+  static std::mutex mu;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
-    (void)cudaGetLastError();
-    per_sm = 1;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < used; ++i)
+      if (table[i].fn == (const void*)kernel && table[i].threads == threads) per_sm = table[i].per_sm;
+    if (per_sm == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+      }
+      if (used < 32) table[used++] = Entry{(const void*)kernel, threads, per_sm};
+    }
   }
   if (per_sm > kLnBwdMaxBlocksPerSm) per_sm = kLnBwdMaxBlocksPerSm;
   const int64_t wave = (int64_t)per_sm * (sm_count_cached() > 0 ? sm_count_cached() : 148);

@@ -56,38 +56,45 @@ inline void check_aligned(const void* p, size_t a, const char* what) {
   }
 }
 
-// run `body()` once per thread of every block, blocks in sequence
+// run `body()` once per thread of every block, blocks in sequence (static `__shared__` storage is one block's at a
+// time).  The OS threads are created once per launch and walk the blocks together; every block gets fresh barriers,
+// so threads that returned early from one block (CUDA: exited threads are not waited for) take part again in the next.
 template <typename Body>
 void launch(Dim3 grid, Dim3 block, Body body) {
   const unsigned nthreads = block.x * block.y * block.z;
   const unsigned nwarps = (nthreads + 31) / 32;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        BlockState st;
-        st.block_bar = std::make_unique<std::barrier<>>(nthreads);
-        for (unsigned w = 0; w < nwarps; ++w) {
-          const unsigned lanes = std::min(32u, nthreads - 32 * w);
-          st.warp_bar.push_back(std::make_unique<std::barrier<>>(lanes));
-        }
-        st.xchg.assign(nthreads, 0);
-        std::vector<std::thread> threads;
-        threads.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t) {
-          threads.emplace_back([&, t]() {
-            t_threadIdx = Dim3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+  const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+  std::vector<BlockState> states(nblocks);
+  for (auto& st : states) {
+    st.block_bar = std::make_unique<std::barrier<>>(nthreads);
+    for (unsigned w = 0; w < nwarps; ++w)
+      st.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - 32 * w)));
+    st.xchg.assign(nthreads, 0);
+  }
+  std::barrier<> next_block(nthreads);
+  std::vector<std::thread> threads;
+  threads.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t) {
+    threads.emplace_back([&, t]() {
+      t_threadIdx = Dim3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      t_blockDim = block;
+      t_gridDim = grid;
+      size_t b = 0;
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx, ++b) {
+            BlockState& st = states[b];
             t_blockIdx = Dim3{bx, by, bz};
-            t_blockDim = block;
-            t_gridDim = grid;
             t_block = &st;
             body();
-            // a thread that has returned no longer takes part in barriers (CUDA: exited threads are not waited for)
+            // a thread that has returned no longer takes part in this block's barriers
             st.warp_bar[t / 32]->arrive_and_drop();
             st.block_bar->arrive_and_drop();
-          });
-        }
-        for (auto& th : threads) th.join();
-      }
+            next_block.arrive_and_wait();
+          }
+    });
+  }
+  for (auto& th : threads) th.join();
 }
 
 inline unsigned linear_tid() {

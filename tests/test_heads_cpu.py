@@ -262,3 +262,43 @@ def test_heads_dtype_runs_the_heads_under_autocast(monkeypatch, fused):
     assert int(bn16.num_batches_tracked) == int(bn32.num_batches_tracked) == 2
     assert rel(bn16.running_mean, bn32.running_mean) < 3e-2
     assert all(p.grad is None or p.grad.dtype == p.dtype for p in m16.parameters())
+
+
+def test_estimator_goldens_through_the_emulated_index_kernel(monkeypatch, golden_dir):
+    """The reference's own estimator semantics (normal, cluster, SSL, hot temperature: tests/golden/estimator_*.npz,
+    written from the unmodified loss.py) through the drop-in module with the index kernel's SOURCE running on the
+    CPU: same check as tests/test_gpu_module.py::test_module_estimator_cases_match_reference_golden, without a GPU."""
+    import glob
+    from clip_lite_b200 import loss as L
+    calls = _emu_backend.install(monkeypatch)
+    monkeypatch.setattr(L.JSDInfoMaxLoss, "_require_cuda", staticmethod(lambda t: None))
+    paths = sorted(glob.glob(os.path.join(golden_dir, "estimator_*.npz")))
+    assert len(paths) >= 5
+    for path in paths:
+        z = np.load(path, allow_pickle=True)
+        ssl = bool(z["ssl"])
+        d = z["in_image_features"].shape[1]
+        m = L.JSDInfoMaxLoss(image_dim=d, text_dim=d, type="dot", image_prior=False, text_prior=False,
+                             visual_self_supervised=ssl, textual_self_supervised=ssl)
+        critics = [m.global_d] + ([m.visual_d, m.textual_d] if ssl else [])
+        for c in critics:
+            c.img_block = torch.nn.Identity()
+            c.text_block = torch.nn.Identity()
+        m.global_d.temperature.data.fill_(float(z["t"]))
+        if ssl:
+            m.visual_d.temperature.data.fill_(float(z["t_ssl"]))
+            m.textual_d.temperature.data.fill_(float(z["t_ssl"]))
+        names = [k[3:] for k in z.files if k.startswith("in_")]
+        leaves = {k: torch.from_numpy(z["in_" + k]).requires_grad_(True) for k in names}
+        out = m(**leaves)
+        out["total_loss"].backward()
+        for k in out:
+            ref = float(z["out_" + k])
+            assert abs(float(out[k].detach()) - ref) <= 1e-5 * max(abs(ref), 1e-30), (path, k)
+        for k in names:
+            assert rel(leaves[k].grad, z["grad_" + k]) < 1e-4, (path, k)
+        assert rel(m.global_d.temperature.grad, z["grad_temperature"]) < 1e-4, path
+        if ssl:
+            assert rel(m.visual_d.temperature.grad, z["grad_temperature_visual"]) < 1e-4
+            assert rel(m.textual_d.temperature.grad, z["grad_temperature_textual"]) < 1e-4
+    assert set(calls) == {"jsd_index_fwd_bwd"}

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One small step of every library path for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
 
-    compute-sanitizer --tool racecheck python tools/sanitize_step.py [dense|index|score|all]
+    compute-sanitizer --tool racecheck python tools/sanitize_step.py [dense|index|score|heads|all]
     compute-sanitizer --tool memcheck  python -m torch.distributed.run --nproc-per-node 2 ... tools/sanitize_step.py peer
 
 Sizes are small (the tools slow kernels down 10-100x) but cover edge tiles (B not a multiple of 256), both CTA-group
@@ -50,6 +50,24 @@ def score():
     print("score ranks", int(r1.sum()), int(r2.sum()), int(col.sum()))
 
 
+def heads(b, d, mode, dtype=torch.float32):
+    """Projection-head tail (jsd_heads.cuh): LayerNorm + normalise fused, forward and backward.  NOT part of "all":
+    these kernels were written after the round-2 logs under profiles/ were taken; run `heads` explicitly."""
+    xf = torch.randn(b, d, device="cuda").to(dtype).requires_grad_(True)
+    xg = torch.randn(b, d, device="cuda").to(dtype).requires_grad_(True)
+    ln_f, ln_g = torch.nn.LayerNorm(d).cuda(), torch.nn.LayerNorm(d).cuda()
+    t = torch.tensor(2.6593, device="cuda", requires_grad=True)
+    if mode == "dense":
+        loss, _ = ops.jsd_dense_loss_ln(xf, xg, ln_f, ln_g, t)
+    else:
+        f, g = ops.ln_normalize_pair(xf, xg, ln_f, ln_g)
+        loss, _ = ops.jsd_index_loss(f, g, t)
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"heads {mode} B={b} D={d} loss={float(loss):.5f} |dX|={float(xf.grad.float().norm()):.4e} "
+          f"|dw|={float(ln_f.weight.grad.norm()):.4e}")
+
+
 def peer():
     import torch.distributed as dist
     from clip_lite_b200 import peer as P
@@ -83,6 +101,11 @@ def main():
         index(256, 512, torch.bfloat16)
     if what in ("score", "all"):
         score()
+    if what == "heads":
+        heads(300, 2048, "index")                     # register-resident forward, two 16-byte pieces per thread backward
+        heads(96, 102, "index", torch.bfloat16)       # element-wise variants
+        heads(256, 128, "dense")                      # fused single-pass kernel's unscaled accumulator slices
+        heads(200, 2176, "dense")                     # staged path, 4-piece backward, generic forward
     if what == "peer":
         peer()
 

@@ -64,7 +64,7 @@ def heads(b, d, mode, dtype=torch.float32):
         loss, _ = ops.jsd_index_loss(f, g, t)
     loss.backward()
     torch.cuda.synchronize()
-    print(f"heads {mode} B={b} D={d} loss={float(loss):.5f} |dX|={float(xf.grad.float().norm()):.4e} "
+    print(f"heads {mode} B={b} D={d} loss={float(loss.detach()):.5f} |dX|={float(xf.grad.float().norm()):.4e} "
           f"|dw|={float(ln_f.weight.grad.norm()):.4e}")
 
 

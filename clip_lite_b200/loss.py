@@ -17,7 +17,11 @@ is where the estimator runs:
 * ``neg_mode="dense"`` switches to the all-pairs estimator on tcgen05 tensor
   cores (``ops.jsd_dense_loss``), ``gather=True`` additionally all-gathers the
   text embeddings across the data-parallel group (``parallel.gathered_dense_loss``).
-  Both default to the reference's behaviour (one rolled negative, per-rank loss).
+  Both default to the reference's behaviour (one rolled negative, per-rank loss);
+* ``fused_heads=True`` moves the LayerNorm that ends each head and the normalisation
+  that follows it (loss.py:36-38, :94-95) into one row pass of libjsd_b200.so per
+  direction (``ops.jsd_dense_loss_ln`` / ``ops.ln_normalize_pair``); ``heads_dtype``
+  runs the heads' GEMMs under bf16 / fp16 autocast.  Both are off by default.
 
 There is no CPU path: calling forward without CUDA tensors raises.
 """

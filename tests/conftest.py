@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout; registered here so that the marker "
+                                       "is known where the plugin is not installed)")
 
 
 def pytest_collection_modifyitems(config, items):

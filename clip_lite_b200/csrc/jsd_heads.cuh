@@ -192,8 +192,12 @@ struct LnNormBwdJob {
   float* rowdot;                       // job 0 only; may be null: <u, dU> per row (their sum = gamma dL/dt)
 };
 
+// Register cap: up to two pieces per thread (D <= 2048, the heads' width) the kernel fits three resident blocks of
+// 256 threads per SM (<= 80 registers; ptxas: at most 24 bytes of spill) -- half as many rows again in flight as the
+// 126 registers the compiler takes when left alone; the four-piece variant would spill 232 bytes there and keeps two
+// resident blocks (128 registers, 16 bytes of spill).
 template <typename T, int VEC, int KCH>
-__global__ void __launch_bounds__(LN_BWD_THREADS)
+__global__ void __launch_bounds__(LN_BWD_THREADS, KCH <= 2 ? 3 : 2)
 ln_normalize_bwd_kernel(const LnNormBwdJob job, int rows, int D, const float* __restrict__ gdiag,
                         const float* __restrict__ t_dev, const float* __restrict__ gamma_dev, float inv_rows) {
   __shared__ float scratch[2 * 32];

@@ -402,12 +402,14 @@ def dense_fused_fwd_bwd(u: torch.Tensor, v: torch.Tensor, t: torch.Tensor):
 
 
 # ------------------------------------------------------------------ projection-head tail (LayerNorm + normalise)
-def _ln_param(p: Optional[torch.Tensor], d: int, name: str) -> Optional[torch.Tensor]:
+def _ln_param(p: Optional[torch.Tensor], d: int, name: str, device=None) -> Optional[torch.Tensor]:
     if p is None:
         return None
     _req(p, name, ndim=1)
     if p.numel() != d:
         raise ValueError(f"{name} must have {d} entries, got {p.numel()}")
+    if device is not None and p.device != device:
+        raise ValueError(f"{name} lives on {p.device}, the rows on {device}")
     return p if p.dtype == torch.float32 else p.float()
 
 
@@ -425,12 +427,14 @@ def ln_normalize_pair(x0: torch.Tensor, x1: Optional[torch.Tensor], ln0, ln1=Non
         _req(x1, "X1", dtype=x0.dtype, ndim=2)
         if x1.shape != x0.shape:
             raise ValueError(f"X0 {tuple(x0.shape)} and X1 {tuple(x1.shape)} must have the same shape")
-    w0, b0, e0 = _ln_param(ln0[0], d, "LayerNorm weight"), _ln_param(ln0[1], d, "LayerNorm bias"), float(ln0[2])
+    dev = x0.device
+    w0, b0, e0 = (_ln_param(ln0[0], d, "LayerNorm weight", dev), _ln_param(ln0[1], d, "LayerNorm bias", dev),
+                  float(ln0[2]))
     w1 = b1 = None
     e1 = 0.0
     if two:
-        w1, b1, e1 = _ln_param(ln1[0], d, "LayerNorm weight"), _ln_param(ln1[1], d, "LayerNorm bias"), float(ln1[2])
-    dev = x0.device
+        w1, b1, e1 = (_ln_param(ln1[0], d, "LayerNorm weight", dev), _ln_param(ln1[1], d, "LayerNorm bias", dev),
+                      float(ln1[2]))
     odt = torch.bfloat16 if out_bf16 else torch.float32
     out = torch.empty(2 if two else 1, rows, d, dtype=odt, device=dev)
     stats = torch.empty(2 if two else 1, 3, rows, dtype=torch.float32, device=dev)
@@ -481,10 +485,10 @@ def ln_normalize_bwd_pair(x0: torch.Tensor, x1: Optional[torch.Tensor], ln0, ln1
             _req(pr, "partner", dtype=torch.bfloat16, ndim=2)
             if pr.shape[1] != d or pr.shape[0] < rows:
                 raise ValueError("partner rows do not cover the row set")
-    w0, b0 = _ln_param(ln0[0], d, "LayerNorm weight"), _ln_param(ln0[1], d, "LayerNorm bias")
+    w0, b0 = _ln_param(ln0[0], d, "LayerNorm weight", dev), _ln_param(ln0[1], d, "LayerNorm bias", dev)
     w1 = b1 = None
     if two:
-        w1, b1 = _ln_param(ln1[0], d, "LayerNorm weight"), _ln_param(ln1[1], d, "LayerNorm bias")
+        w1, b1 = _ln_param(ln1[0], d, "LayerNorm weight", dev), _ln_param(ln1[1], d, "LayerNorm bias", dev)
     tt = None if t is None else _scalar(t, "temperature")
     gg = None if gamma is None else _scalar(gamma, "gamma")
     dx = [torch.empty_like(x0), torch.empty_like(x1) if two else None]

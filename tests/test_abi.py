@@ -193,3 +193,16 @@ def test_head_tail_entry_points_validate_before_launching(lib):
     assert rc != 0 and b"positive-pair" in lib.jsd_last_error()
     assert lib.jsd_ln_workspace_bytes(4, 64) == 2 * 4 * 2 * 64 * 4          # never more blocks than rows
     assert lib.jsd_ln_workspace_bytes(0, 64) == 0
+
+
+def test_product_build_never_enables_the_cpu_emulation():
+    """JSD_HOST_EMU (tests/emu: kernel source compiled for the CPU) is a test-tier switch: the product's nvcc command
+    does not define it, no product module mentions it, and the shipped library exports no emulation entry point."""
+    from clip_lite_b200 import build
+    assert not any("JSD_HOST_EMU" in f for f in build.NVCC_FLAGS)
+    pkg = os.path.join(ROOT, "clip_lite_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            assert "emu" not in open(os.path.join(pkg, name)).read().lower(), name
+    lib = ctypes.CDLL(build.build_library())
+    assert not hasattr(lib, "emu_ln_normalize_pair") and not hasattr(lib, "emu_set_bwd_blocks")

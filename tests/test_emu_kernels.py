@@ -355,3 +355,31 @@ def test_head_tail_kernels_are_memcheck_clean_under_asan(tmp_path):
                         env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
     assert ok.returncode == 0, (ok.stdout[-500:], ok.stderr[-3000:])
     assert "racecheck cases done rc=0" in ok.stdout
+
+
+def test_ln_tail_full_size_with_the_production_launch_shape(emu):
+    """The heads' real shape -- B = 8192 rows of D = 2048 (the bench's index workload; the module's width) -- with the
+    launch the product makes on a B200: register-resident forward, backward with 256 threads x two 16-byte pieces
+    and 3 x 148 = 444 blocks walking ~18 rows each, column partials summed over 444 blocks."""
+    rows, d, blocks = 8192, 2048, 444
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(rows, d, generator=g) * 1.5 + 0.3
+    w, b = make_ln(d, 21)
+    out, st = torch.empty(rows, d), torch.empty(3, rows)
+    assert emu.emu_ln_normalize_pair(ptr(x), None, 0, rows, d, ptr(w), ptr(b), 1e-5, None, None, 0.0, 0, ptr(out), None,
+                                     ptr(st), None, -1) == 0
+    u, mean, rstd, inv = ln_unit_reference(x, w, b, 1e-5)
+    assert float((out.double() - u).abs().max()) < 1e-6
+    assert rel(st[0], mean) < 1e-5 and rel(st[1], rstd) < 1e-5 and rel(st[2], inv) < 1e-5
+    du = torch.randn(rows, d, generator=g)
+    ws = torch.full((2 * blocks * 2 * d,), float("nan"))
+    dx, dw, db = torch.empty_like(x), torch.empty(d), torch.empty(d)
+    rowdot, dt = torch.empty(rows), torch.empty(1)
+    got = emu.emu_ln_normalize_bwd_pair(ptr(x), None, 0, rows, d, ptr(w), ptr(b), None, None, ptr(st), None, ptr(du),
+                                        None, 1, 0, 0.0, None, 0, None, 0, None, None, None, rows, ptr(ws), ptr(dx),
+                                        None, ptr(dw), ptr(db), None, None, ptr(rowdot), ptr(dt), blocks, 0)
+    assert got == 4000 + 256 * 10 + 2
+    rdx, rdw, rdb, rdot = ln_bwd_reference(x, w, b, 1e-5, du.double())
+    assert rel(dx, rdx) < 2e-5 and rel(dw, rdw) < 1e-5 and rel(db, rdb) < 1e-5
+    assert rel(rowdot, rdot) < 1e-5
+    assert abs(float(dt) - float(rdot.sum())) < 1e-6 * float(rdot.abs().sum())

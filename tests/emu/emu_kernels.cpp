@@ -119,6 +119,7 @@ int emu_ln_normalize_bwd_pair(const void* X0, const void* X1, int dtype, long lo
   return rc;
 }
 
+#ifndef EMU_HEADS_ONLY   // (the sanitizer builds instantiate the head-tail kernels only: a third of the compile time)
 // ---- kernels that ARE covered by the GPU tier, run here to validate the shim itself against the oracle
 int emu_normalize_cast(const void* X, int dtype, long long rows, long long D, void* Xn_bf16, float* inv_norm,
                        int variant /* 0 reg, 1 vec4, 2 scalar */) {
@@ -183,6 +184,8 @@ int emu_index_fwd_bwd(const void* F, const void* G, int dtype, long long B, long
   EMU_DISPATCH(dtype, run(T{}));
 }
 
+#endif  // !EMU_HEADS_ONLY
+
 // ---- the head-tail entry points under their PRODUCT names and signatures (include/jsd_b200.h), so that
 // clip_lite_b200/kernels.py can be run unmodified against this library on CPU tensors (tests/test_heads_cpu.py):
 // a wrong argument order in the 34-argument ctypes call shows up here, not on the GPU.  `stream` is ignored.
@@ -217,6 +220,7 @@ int jsd_ln_normalize_bwd_pair(const void* X0, const void* X1, int dtype, int64_t
                                    db0, dw1, db1, rowdot, dt_out, blocks, 0) >= 0 ? 0 : 1;
 }
 
+#ifndef EMU_HEADS_ONLY
 // index mode under its product name (the L1-based kernel; the ring-staged kernel needs the bulk-copy engine), so
 // that a whole index-mode step of the drop-in module can run through kernels.py on CPU tensors
 size_t jsd_index_workspace_bytes(int64_t B) { return (size_t)(B > 0 ? B : 0) * 4 * sizeof(float); }
@@ -234,5 +238,7 @@ int jsd_index_fwd_bwd(const void* F, const void* G, int dtype, int64_t B, int64_
   if (rc == 0 && loss_out) *loss_out = out4[2];
   return rc;
 }
+
+#endif  // !EMU_HEADS_ONLY
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 // or global-memory access that is not ordered by a barrier -- what compute-sanitizer --tool racecheck reports on the
 // GPU -- is a data race TSan reports here.  Built with -fsanitize=thread by tests/test_emu_kernels.py; exits non-zero
 // when TSan saw a race (TSAN_OPTIONS=halt_on_error=1 exitcode=66) or a result is not finite.
+#define EMU_HEADS_ONLY 1
 #include "emu_kernels.cpp"
 
 #include <random>

@@ -11,6 +11,7 @@ import ctypes
 import pytest
 import torch
 
+from oracle import heads_oracle as ho
 from oracle import jsd_oracle as orc
 
 from tests import _emu_backend
@@ -124,13 +125,10 @@ def test_shim_index_kernel_matches_oracle(emu, b, d, vec, mode):
 
 # ------------------------------------------------------------------ projection-head tail: forward
 def ln_unit_reference(x, w, b, eps):
-    x = x.double()
-    y = torch.nn.functional.layer_norm(x, x.shape[-1:], None if w is None else w.double(),
-                                       None if b is None else b.double(), eps)
-    n = y.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-    mean = x.mean(-1)
-    rstd = 1.0 / torch.sqrt(x.var(-1, unbiased=False) + eps)
-    return y / n, mean, rstd, 1.0 / n.squeeze(-1)
+    """(unit rows, mean, rstd, 1/||LN(x)||) by the fp64 oracle (oracle/heads_oracle.py <- loss.py:36-38, :94-95)."""
+    u, (mean, rstd, inv) = ho.ln_unit(x.double(), None if w is None else w.double(),
+                                      None if b is None else b.double(), eps)
+    return u, mean, rstd, inv
 
 
 def make_ln(d, seed, affine=True):
@@ -196,17 +194,10 @@ def test_ln_normalize_forward_zero_variance_row_is_finite(emu):
 
 # ------------------------------------------------------------------ projection-head tail: backward
 def ln_bwd_reference(x, w, b, eps, du):
-    """dx, dw, db, <u, dU> of sum(u * dU) with u = LN(x) / ||LN(x)|| by fp64 autograd."""
-    x = x.double().requires_grad_(True)
-    d = x.shape[-1]
-    w_ = torch.ones(d, dtype=torch.float64) if w is None else w.double()
-    b_ = torch.zeros(d, dtype=torch.float64) if b is None else b.double()
-    w_.requires_grad_(True)
-    b_.requires_grad_(True)
-    y = torch.nn.functional.layer_norm(x, (d,), w_, b_, eps)
-    u = y / y.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-    (u * du).sum().backward()
-    return x.grad, w_.grad, b_.grad, (u.detach() * du).sum(-1)
+    """(dx, dw, db, <u, dU>) for the upstream gradient dU by the fp64 oracle's closed forms (pinned against
+    autograd of the reference's ops in tests/test_oracle.py)."""
+    return ho.ln_unit_grads(x.double(), None if w is None else w.double(), None if b is None else b.double(), eps,
+                            du.double())
 
 
 def run_ln_fwd(emu, xs, lns, eps):

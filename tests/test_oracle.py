@@ -160,3 +160,52 @@ def test_softplus_threshold_and_edge_cases():
     assert torch.equal(z, torch.zeros(2, 4)) and float(n[0]) == pytest.approx(1e-12)
     assert orc.shift1_index(1).tolist() == [0]
     assert orc.cluster_index(3).tolist() == [3, 4, 5, 1, 2, 0]
+
+
+# ------------------------------------------------------------------ projection-head tail
+@pytest.mark.parametrize("affine", [True, False])
+@pytest.mark.parametrize("rows,d", [(7, 16), (33, 100), (4, 2048)])
+def test_heads_oracle_closed_forms_equal_autograd_of_the_reference_ops(rows, d, affine):
+    """oracle.heads_oracle against fp64 autograd of nn.LayerNorm (loss.py:36-38) + F.normalize (loss.py:94-95)."""
+    from oracle import heads_oracle as ho
+    g = torch.Generator().manual_seed(rows * d)
+    x = (torch.randn(rows, d, generator=g, dtype=torch.float64) * 1.7 + 0.4).requires_grad_(True)
+    ln = torch.nn.LayerNorm(d, eps=1e-5, elementwise_affine=affine).double()
+    if affine:
+        with torch.no_grad():
+            ln.weight.copy_(1.0 + 0.3 * torch.randn(d, generator=g, dtype=torch.float64))
+            ln.bias.copy_(0.2 * torch.randn(d, generator=g, dtype=torch.float64))
+    du = torch.randn(rows, d, generator=g, dtype=torch.float64)
+    ref_u = torch.nn.functional.normalize(ln(x), p=2, dim=-1)
+    (ref_u * du).sum().backward()
+    w, b = (ln.weight.detach(), ln.bias.detach()) if affine else (None, None)
+    u, (mean, rstd, inv) = ho.ln_unit(x.detach(), w, b, ln.eps)
+    dx, dw, db, rowdot = ho.ln_unit_grads(x.detach(), w, b, ln.eps, du)
+    assert (u - ref_u).abs().max() < 1e-14
+    assert (dx - x.grad).abs().max() < 1e-12 * x.grad.abs().max().clamp_min(1.0)
+    if affine:
+        assert (dw - ln.weight.grad).abs().max() < 1e-12 * ln.weight.grad.abs().max().clamp_min(1.0)
+        assert (db - ln.bias.grad).abs().max() < 1e-12 * ln.bias.grad.abs().max().clamp_min(1.0)
+    assert (rowdot - (ref_u.detach() * du).sum(-1)).abs().max() < 1e-13
+    assert (mean - x.detach().mean(-1)).abs().max() < 1e-14 and (inv - 1.0 / ln(x).detach().norm(dim=-1)).abs().max() < 1e-12
+    assert (rstd - 1.0 / torch.sqrt(x.detach().var(-1, unbiased=False) + ln.eps)).abs().max() < 1e-13
+
+
+@pytest.mark.skipif(not rl.reference_available(), reason="needs /root/reference (build container)")
+def test_heads_oracle_matches_the_live_reference_head():
+    """The reference's own MILinearBlock (loss.py:12-40) followed by its F.normalize (loss.py:94-95): the oracle's
+    ln_unit applied to the head's pre-LayerNorm sum reproduces the unit rows the reference's dot critic scores."""
+    from oracle import heads_oracle as ho
+    ref = rl.load_reference_loss()
+    torch.manual_seed(0)
+    block = ref.MILinearBlock(24, units=64).double().eval()
+    with torch.no_grad():
+        block.feature_block_ln.weight.uniform_(0.5, 1.5)
+        block.feature_block_ln.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(9, 24, dtype=torch.float64)
+    with torch.no_grad():
+        want = torch.nn.functional.normalize(block(x), p=2, dim=-1)          # loss.py:91-95 on one head
+        pre = block.feature_nonlinear(x) + block.feature_shortcut(x)         # loss.py:36
+    ln = block.feature_block_ln
+    got, _ = ho.ln_unit(pre, ln.weight.detach(), ln.bias.detach(), ln.eps)
+    assert (got - want).abs().max() < 1e-13

@@ -13,6 +13,7 @@ import pytest
 import torch
 
 from _weights import seeded_state_dict
+from oracle import heads_oracle as ho
 from oracle import jsd_oracle as orc
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
@@ -53,22 +54,17 @@ def make_ln(d, seed, affine=True):
 
 
 def ln_unit_reference(x, w, b, eps):
-    x = x.double()
-    y = torch.nn.functional.layer_norm(x, x.shape[-1:], None if w is None else w.double(),
-                                       None if b is None else b.double(), eps)
-    n = y.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-    return y / n, x.mean(-1), 1.0 / torch.sqrt(x.var(-1, unbiased=False) + eps), 1.0 / n.squeeze(-1)
+    """(unit rows, mean, rstd, 1/||LN(x)||) by the fp64 oracle (oracle/heads_oracle.py <- loss.py:36-38, :94-95)."""
+    u, (mean, rstd, inv) = ho.ln_unit(x.double(), None if w is None else w.double(),
+                                      None if b is None else b.double(), eps)
+    return u, mean, rstd, inv
 
 
 def ln_bwd_reference(x, w, b, eps, du):
-    x = x.double().requires_grad_(True)
-    d = x.shape[-1]
-    w_ = (torch.ones(d, dtype=torch.float64, device=x.device) if w is None else w.double()).requires_grad_(True)
-    b_ = (torch.zeros(d, dtype=torch.float64, device=x.device) if b is None else b.double()).requires_grad_(True)
-    y = torch.nn.functional.layer_norm(x, (d,), w_, b_, eps)
-    u = y / y.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-    (u * du).sum().backward()
-    return x.grad, w_.grad, b_.grad, (u.detach() * du).sum(-1)
+    """(dx, dw, db, <u, dU>) for the upstream gradient dU by the fp64 oracle's closed forms (pinned against
+    autograd of the reference's ops in tests/test_oracle.py)."""
+    return ho.ln_unit_grads(x.double(), None if w is None else w.double(), None if b is None else b.double(), eps,
+                            du.double())
 
 
 # ------------------------------------------------------------------ kernels through the C ABI
